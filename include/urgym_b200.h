@@ -1,0 +1,137 @@
+/* urgym_b200.h -- C ABI of the B200-native batched simulator for UR-gym's reach-task step path.
+ *
+ * Drop-in boundary.  The reference (pure Python) has no FFI of its own: its hot path sits behind the Gymnasium
+ * Env protocol of `RobotTaskEnv` (UR_gym/envs/core.py:222-317) and, inside it, behind `class PyBullet`
+ * (UR_gym/pyb_setup.py:15), one physics client per env.  This library replaces pyb_setup.py + the arithmetic of
+ * envs/robots/UR5.py and envs/tasks/reach.py for N environments at once; the Python host layer in
+ * ur-gym_b200/ binds it with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C: opaque handle, raw pointers, sizes; no torch / C++ types in any signature.
+ *   - every function returns 0 on success, a negative URGYM_E* code otherwise; urgym_last_error() gives text.
+ *     The library never exits or aborts; CUDA errors are reported, not swallowed.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry points are
+ *     stream-ordered and asynchronous: they enqueue work and return without synchronising the device.
+ *   - all "device" pointers are caller-owned device memory (row-major, contiguous, 16-byte aligned for the
+ *     bulk-copy fast path; unaligned pointers take a slower but equivalent path).  The library allocates only its
+ *     persistent structure-of-arrays state at urgym_create().
+ *   - one handle per GPU per process; a handle is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device urgym_create() fails with URGYM_ENODEVICE.
+ */
+#ifndef URGYM_B200_H
+#define URGYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct urgym_env urgym_env_t;
+
+/* task ids: the four registered envs in scope (UR_gym/__init__.py:19-42, UR_gym/envs/ur_tasks.py:37-90) */
+enum { URGYM_TASK_ORI = 0,   /* UR5OriReach-v1  ReachOri  reach.py:141-236  obs 18, goal 6 */
+       URGYM_TASK_OBS = 1,   /* UR5ObsReach-v1  ReachObs  reach.py:239-374  obs 26, goal 3 */
+       URGYM_TASK_STA = 2,   /* UR5StaReach-v1  ReachSta  reach.py:377-573  obs 29, goal 6 */
+       URGYM_TASK_DYN = 3 }; /* UR5DynReach-v1  ReachDyn  reach.py:576-785  obs 35, goal 6 */
+
+/* link geometry used by getClosestPoints stand-ins (pyb_setup.py:382-456) */
+enum { URGYM_GEOM_HULL = 0,     /* the reference's convex-hull links + cylinder/box scene, GJK distances */
+       URGYM_GEOM_CAPSULE = 1 };/* bounding capsules for links, capsule obstacle: closed-form distances (approximate) */
+
+/* state fields for urgym_get_state / urgym_set_state: the injection hooks of the reference
+ * (robot.set_joint_angles core.py:161-167; task.set_goal reach.py:202-204; task.set_goal_and_obstacle
+ * reach.py:328-335,483-503,702-713) and a checkpoint of the whole simulator. */
+enum { URGYM_F_Q = 0,            /* float [N,6]  joint angles                                  */
+       URGYM_F_GOAL = 1,         /* float [N,G]  goal (pos[,euler]); G = urgym_goal_dim()      */
+       URGYM_F_OBSTACLE = 2,     /* float [N,6]  obstacle pose pos+euler (Dyn: obstacle_start) */
+       URGYM_F_OBSTACLE_END = 3, /* float [N,6]  Dyn obstacle_end                              */
+       URGYM_F_LINK_DIST = 4,    /* float [N,5]  link_dist == last_dist (reach.py:324,479,681) */
+       URGYM_F_ELAPSED = 5,      /* int32 [N]    TimeLimit counter == ReachDyn.step_num        */
+       URGYM_F_EP_RETURN = 6,    /* float [N]    running episode return                        */
+       URGYM_F_EPISODE = 7,      /* uint32 [N]   episode counter (RNG stream position)         */
+       URGYM_F_VELOCITY = 8,     /* float [N,6]  ReachDyn.velocity as last set (stale after reset: reach.py:664-683) */
+       URGYM_F_COUNT = 9 };
+
+#define URGYM_OK 0
+#define URGYM_EINVAL (-1)     /* bad argument                         */
+#define URGYM_ENODEVICE (-2)  /* no usable CUDA device                */
+#define URGYM_ECUDA (-3)      /* a CUDA runtime call failed           */
+#define URGYM_ENOMEM (-4)     /* allocation failed                    */
+#define URGYM_EUNSUPPORTED (-5)
+
+#define URGYM_MAX_EPISODE_STEPS 100   /* register(max_episode_steps=100)  UR_gym/__init__.py:22,28,34,41 */
+#define URGYM_STATS_COUNT 8
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+/* n_envs environments with global indices [env_index_offset, env_index_offset + n_envs) on CUDA device `device`.
+ * `seed` keys the counter-based reset stream; results depend on (seed, global env index, episode), not on the
+ * sharding.  All envs start un-reset: call urgym_reset(h, NULL, ...) once.   Replaces: gymnasium.make(id)
+ * (ur_tasks.py:37-90: PyBullet(...) + UR5Ori(...) + Reach*(...)). */
+int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_envs, int64_t env_index_offset,
+                 uint64_t seed, int device);
+int urgym_destroy(urgym_env_t *h);                       /* RobotTaskEnv.close  core.py:319-320 */
+const char *urgym_last_error(const urgym_env_t *h);      /* h may be NULL: error of the last failed create */
+
+int urgym_obs_dim(int task);    /* 18 / 26 / 29 / 35 */
+int urgym_goal_dim(int task);   /* 6 / 3 / 6 / 6     */
+int64_t urgym_num_envs(const urgym_env_t *h);
+
+/* ---- the hot path ---------------------------------------------------------------------------------------- */
+/* One env step for every env, then auto-reset of the envs that finished (SB3 DummyVecEnv semantics, which is what
+ * train.py's loop sees: train.py:39-60).            Replaces: RobotTaskEnv.step  core.py:303-317 (+ TimeLimit)
+ *   actions      [N,6] float  in   clipped to [-1,1] inside                              UR5.py:273-279
+ *   obs          [N,D] float  out  next observation; for finished envs the first observation of the new episode
+ *   achieved     [N,G] float  out  achieved_goal belonging to `obs`
+ *   desired      [N,G] float  out  desired_goal belonging to `obs` (may be NULL: read URGYM_F_GOAL instead)
+ *   reward       [N]   float  out
+ *   terminated   [N]   uint8  out  success or collision                                  core.py:313
+ *   truncated    [N]   uint8  out  elapsed >= 100 (TimeLimit)                            UR_gym/__init__.py
+ *   is_success   [N]   uint8  out  info["is_success"]                                    core.py:315
+ *   terminal_obs [N,D] float  out  rows of finished envs only: the observation of the final step
+ *                                  (DummyVecEnv's info["terminal_observation"]); may be NULL
+ *   terminal_achieved [N,G] float out  likewise; may be NULL                                                    */
+int urgym_step(urgym_env_t *h, const float *actions, float *obs, float *achieved, float *desired, float *reward,
+               uint8_t *terminated, uint8_t *truncated, uint8_t *is_success, float *terminal_obs,
+               float *terminal_achieved, void *stream);
+
+/* Reset the envs whose mask byte is non-zero (mask == NULL: all).  Writes the first observation of the new episode
+ * into the rows of obs/achieved/desired it resets (any of them may be NULL).
+ *                                                      Replaces: RobotTaskEnv.reset  core.py:263-273 */
+int urgym_reset(urgym_env_t *h, const uint8_t *mask, float *obs, float *achieved, float *desired, void *stream);
+
+/* Recompute obs / achieved / desired from the current state without stepping (any may be NULL).
+ *                                                      Replaces: RobotTaskEnv._get_obs  core.py:252-261 */
+int urgym_observe(urgym_env_t *h, float *obs, float *achieved, float *desired, void *stream);
+
+/* After injecting goal / obstacle / joints with urgym_set_state: recompute link_dist (= last_dist) and report the
+ * collision flag, as the tail of set_goal_and_obstacle does (reach.py:333-335,501-503,711-713).
+ * collision [N] uint8 out, may be NULL. */
+int urgym_refresh(urgym_env_t *h, uint8_t *collision, void *stream);
+
+/* ---- state access (device pointers, stream-ordered) ------------------------------------------------------- */
+int urgym_get_state(urgym_env_t *h, int field, void *dst, void *stream);
+int urgym_set_state(urgym_env_t *h, int field, const void *src, void *stream);
+
+/* Episode statistics accumulated on the device since the last call with reset_after != 0; synchronises `stream`.
+ *   out[0] episodes finished   out[1] sum of episode returns   out[2] sum of episode lengths
+ *   out[3] successes           out[4] collisions               out[5] truncations
+ *   out[6] env steps taken     out[7] reset rejection iterations
+ * These are the per-shard sums that the host layer all-reduces over ranks. */
+int urgym_stats(urgym_env_t *h, double out[URGYM_STATS_COUNT], int reset_after, void *stream);
+
+/* ---- host-buffer entry point (what a CPU-side caller such as SB3's DummyVecEnv replacement uses) ----------- */
+/* Same as urgym_step but every pointer is HOST memory (pageable or pinned); copies actions to the device, steps,
+ * copies the results back and synchronises.  desired/terminal_* may be NULL. */
+int urgym_step_host(urgym_env_t *h, const float *actions, float *obs, float *achieved, float *desired,
+                    float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
+                    float *terminal_obs, float *terminal_achieved);
+int urgym_reset_host(urgym_env_t *h, const uint8_t *mask, float *obs, float *achieved, float *desired);
+
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t urgym_launch_count(const urgym_env_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* URGYM_B200_H */
