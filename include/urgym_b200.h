@@ -49,9 +49,8 @@ enum { URGYM_F_Q = 0,            /* float [N,6]  joint angles                   
        URGYM_F_LINK_DIST = 4,    /* float [N,5]  link_dist == last_dist (reach.py:324,479,681) */
        URGYM_F_ELAPSED = 5,      /* int32 [N]    TimeLimit counter == ReachDyn.step_num        */
        URGYM_F_EP_RETURN = 6,    /* float [N]    running episode return                        */
-       URGYM_F_EPISODE = 7,      /* uint32 [N]   episode counter (RNG stream position)         */
-       URGYM_F_VELOCITY = 8,     /* float [N,6]  ReachDyn.velocity as last set (stale after reset: reach.py:664-683) */
-       URGYM_F_COUNT = 9 };
+       URGYM_F_VELOCITY = 7,     /* float [N,6]  ReachDyn.velocity carried over the last reset (reach.py:664-683 never clears it) */
+       URGYM_F_COUNT = 8 };
 
 #define URGYM_OK 0
 #define URGYM_EINVAL (-1)     /* bad argument                         */
@@ -65,8 +64,10 @@ enum { URGYM_F_Q = 0,            /* float [N,6]  joint angles                   
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
 /* n_envs environments with global indices [env_index_offset, env_index_offset + n_envs) on CUDA device `device`.
- * `seed` keys the counter-based reset stream; results depend on (seed, global env index, episode), not on the
- * sharding.  All envs start un-reset: call urgym_reset(h, NULL, ...) once.   Replaces: gymnasium.make(id)
+ * `seed` keys the counter-based reset stream (Philox4x32-10): the draws of a reset depend on (seed, global env
+ * index, reset event), where the reset event is the handle's count of urgym_step/urgym_reset calls so far -- not on
+ * the sharding, so 1/2/4/8-GPU runs that issue the same calls produce the same episodes.
+ * All envs start un-reset: call urgym_reset(h, NULL, ...) once.   Replaces: gymnasium.make(id)
  * (ur_tasks.py:37-90: PyBullet(...) + UR5Ori(...) + Reach*(...)). */
 int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_envs, int64_t env_index_offset,
                  uint64_t seed, int device);
@@ -127,6 +128,14 @@ int urgym_step_host(urgym_env_t *h, const float *actions, float *obs, float *ach
                     float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
                     float *terminal_obs, float *terminal_achieved);
 int urgym_reset_host(urgym_env_t *h, const uint8_t *mask, float *obs, float *achieved, float *desired);
+
+/* ---- options / checkpoint scalars ---------------------------------------------------------------------------- */
+/* auto-reset on (default, DummyVecEnv semantics) or off (a bare RobotTaskEnv: finished envs keep their state and
+ * keep stepping until the caller resets them, core.py:303-317). */
+int urgym_set_autoreset(urgym_env_t *h, int enabled);
+/* the reset-event counter (position of the reset stream); together with the URGYM_F_* fields it checkpoints a handle */
+int urgym_get_event(const urgym_env_t *h, uint32_t *event);
+int urgym_set_event(urgym_env_t *h, uint32_t event);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t urgym_launch_count(const urgym_env_t *h);

@@ -146,9 +146,10 @@ def philox4x32_10(counter, key):
 
 
 class UniformStream:
-    """u(slot) for rejection iteration k of episode e of env i."""
+    """u(slot) for rejection iteration k of the reset that env i performs at reset event e (the product counts its
+    step/reset calls; every reset that happens inside call number e draws from position e)."""
 
-    def begin(self, env_index: int, episode: int, blocks_per_iter: int) -> None:
+    def begin(self, env_index: int, event: int, blocks_per_iter: int) -> None:
         raise NotImplementedError
 
     def iteration(self, k: int) -> None:
@@ -159,14 +160,14 @@ class UniformStream:
 
 
 class PhiloxStream(UniformStream):
-    """The kernels' stream: counter = (k*blocks_per_iter + slot//4, episode, env_index, 0), key = seed (lo, hi);
+    """The kernels' stream: counter = (k*blocks_per_iter + slot//4, event, env_index lo, hi), key = seed (lo, hi);
     u = (x >> 8) * 2**-24, exactly representable in float32."""
 
     def __init__(self, seed: int):
         self.key = (seed & _M32, (seed >> 32) & _M32)
 
-    def begin(self, env_index, episode, blocks_per_iter):
-        self.env, self.ep, self.bpi, self.k, self._cache = env_index, episode, blocks_per_iter, 0, {}
+    def begin(self, env_index, event, blocks_per_iter):
+        self.env, self.ep, self.bpi, self.k, self._cache = env_index, event, blocks_per_iter, 0, {}
 
     def iteration(self, k):
         self.k, self._cache = k, {}
@@ -185,7 +186,7 @@ class NumpyStream(UniformStream):
     def __init__(self, seed: Optional[int] = None):
         self.rng = np.random.default_rng(seed)
 
-    def begin(self, env_index, episode, blocks_per_iter):
+    def begin(self, env_index, event, blocks_per_iter):
         pass
 
     def iteration(self, k):
@@ -479,10 +480,11 @@ class ReachTask:
         return np.concatenate((pos, rot))
 
     # ---- reset
-    def reset(self) -> None:
+    def reset(self, event: Optional[int] = None) -> None:
         S = SLOTS[self.kind]
-        self.stream.begin(self.env_index, self.episode, self.p["bpi"])
         self.episode += 1
+        self.stream.begin(self.env_index, self.episode if event is None else event, self.p["bpi"])
+        self.min_reject_margin = np.inf        # how close any rejection decision of this reset was to its threshold
         self.collision = False
         if self.kind == "Ori":                                          # reach.py:197-200
             self.stream.iteration(0)
@@ -501,7 +503,9 @@ class ReachTask:
                 self.sim.set_base_pose("target", self.goal[:3], self.goal[3:])
                 self.sim.set_base_pose("obstacle", self.obstacle_end[:3], self.obstacle_end[3:])
                 start_end = distance(self.obstacle_end, self.obstacle_start)
-                fail = (self.sim.get_target_to_obstacle_distance() < 0.1) or bool(start_end < 1)
+                t2o = self.sim.get_target_to_obstacle_distance()
+                self.min_reject_margin = min(self.min_reject_margin, abs(t2o - 0.1), abs(float(start_end[0]) - 1.0))
+                fail = (t2o < 0.1) or bool(start_end < 1)
             else:                                                       # reach.py:316-321, 468-473
                 self.goal = self._sample_goal(S)
                 self.obstacle = self._sample_obstacle(S)
@@ -510,7 +514,9 @@ class ReachTask:
                 else:
                     self.sim.set_base_pose("target", self.goal[:3], self.goal[3:])
                 self.sim.set_base_pose("obstacle", self.obstacle[:3], self.obstacle[3:])
-                fail = self.sim.get_target_to_obstacle_distance() < 0.1
+                t2o = self.sim.get_target_to_obstacle_distance()
+                self.min_reject_margin = min(self.min_reject_margin, abs(t2o - 0.1))
+                fail = t2o < 0.1
             k += 1
             if not fail or k >= MAX_RESET_ITERS:
                 break
@@ -628,14 +634,14 @@ class OracleEnv:
     max_episode_steps = 100
 
     def __init__(self, env_id: str, geom: int = GEOM_HULL, stream: Optional[UniformStream] = None,
-                 env_index: int = 0):
+                 env_index: int = 0, first_event: Optional[int] = None):
         assert env_id in TASKS, env_id
         self.spec_id = env_id
         self.sim = OracleSim(geom=geom)
         self.robot = UR5Ori(self.sim)
         self.task = ReachTask(self.sim, self.robot, env_id, stream or NumpyStream(0), env_index)
         self._elapsed_steps = 0
-        self.reset()                                                    # core.py:237
+        self.reset(event=first_event)                                   # core.py:237
 
     def _get_obs(self) -> Dict[str, np.ndarray]:                        # core.py:252-261
         robot_obs = self.robot.get_obs().astype(np.float32)
@@ -644,10 +650,10 @@ class OracleEnv:
                 "achieved_goal": self.task.get_achieved_goal().astype(np.float32),
                 "desired_goal": self.task.get_goal().astype(np.float32)}
 
-    def reset(self, seed=None, options=None):                           # core.py:263-273
+    def reset(self, seed=None, options=None, event: Optional[int] = None):   # core.py:263-273
         self._elapsed_steps = 0
         self.robot.reset()
-        self.task.reset()
+        self.task.reset(event)
         obs = self._get_obs()
         return obs, {"is_success": self.task.is_success(obs["achieved_goal"], self.task.get_goal())}
 

@@ -33,8 +33,12 @@
  *   with *deep = 1 and distance = -(marginA+marginB) (penetration depth of the cores taken as 0).
  *
  * Geometry modes:  ORC_GEOM_HULL    links are the reference's convex hulls (margin 0.001)
- *                  ORC_GEOM_CAPSULE links are the extractor's bounding capsules (segment core, margin = r);
- *                                   this is the product's throughput geometry, not the reference's.
+ *                  ORC_GEOM_CAPSULE the product's throughput geometry, not the reference's: links are the
+ *                                   extractor's bounding capsules (segment core, margin = r + hull margin, so a
+ *                                   capsule distance never exceeds the hull distance), the obstacle cylinder is its
+ *                                   bounding capsule (segment half length 0.2, margin 0.05), the target is a sphere
+ *                                   (Obs: r 0.02 as in the reference; Sta/Dyn: the cube's bounding sphere);
+ *                                   table and track stay the reference's boxes.
  */
 #include <math.h>
 #include <string.h>
@@ -277,7 +281,23 @@ static void closest_tri(const double *a, const double *b, const double *c, doubl
     if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
         double w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); lam[0] = 0; lam[1] = 1 - w; lam[2] = w; return;
     }
-    double den = 1.0 / (va + vb + vc), v = vb * den, w = vc * den;
+    double sum = va + vb + vc;
+    if (!(sum > 0.0)) {
+        /* degenerate (collinear) triangle: the closest point is on one of the edges */
+        const double *P[3] = {a, b, c};
+        double best = 1e300;
+        for (int e = 0; e < 3; e++) {
+            const double *p = P[e], *q = P[(e + 1) % 3];
+            double pq[3]; sub3(q, p, pq);
+            double den = dot3(pq, pq), t = den > 0 ? -dot3(p, pq) / den : 0.0;
+            t = t < 0 ? 0 : (t > 1 ? 1 : t);
+            double x[3] = {p[0] + t * pq[0], p[1] + t * pq[1], p[2] + t * pq[2]};
+            double dd = dot3(x, x);
+            if (dd < best) { best = dd; lam[0] = lam[1] = lam[2] = 0; lam[e] = 1 - t; lam[(e + 1) % 3] = t; }
+        }
+        return;
+    }
+    double den = 1.0 / sum, v = vb * den, w = vc * den;
     lam[0] = 1 - v - w; lam[1] = v; lam[2] = w;
 }
 
@@ -304,9 +324,14 @@ static int closest_simplex(double W[4][3], int *n, double v[3]) {
     } else {
         static const int F[4][4] = {{0, 1, 2, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {1, 3, 2, 0}};
         double best = 1e300; int any = 0;
+        /* a (numerically) flat tetrahedron encloses nothing: look at all four faces */
+        double e1[3], e2[3], e3[3], cr[3];
+        sub3(W[1], W[0], e1); sub3(W[2], W[0], e2); sub3(W[3], W[0], e3); cross3(e1, e2, cr);
+        double det = dot3(cr, e3), L2 = fmax(fmax(dot3(e1, e1), dot3(e2, e2)), dot3(e3, e3));
+        int flat = det * det <= 1e-24 * L2 * L2 * L2;
         for (int f = 0; f < 4; f++) {
             const int *id = F[f];
-            if (!origin_outside(W[id[0]], W[id[1]], W[id[2]], W[id[3]])) continue;
+            if (!flat && !origin_outside(W[id[0]], W[id[1]], W[id[2]], W[id[3]])) continue;
             double l3[3], p[3];
             closest_tri(W[id[0]], W[id[1]], W[id[2]], l3);
             for (int k = 0; k < 3; k++) p[k] = l3[0] * W[id[0]][k] + l3[1] * W[id[1]][k] + l3[2] * W[id[2]][k];
@@ -341,7 +366,7 @@ static double gjk_core_distance(const shape_t *A, const shape_t *B, int *deep, i
     double nd[3] = {-d[0], -d[1], -d[2]};
     support(A, nd, sa); support(B, d, sb); sub3(sa, sb, v);
     memcpy(W[0], v, sizeof(v)); n = 1;
-    double vv = dot3(v, v);
+    double vv = dot3(v, v), lb = 0.0;    /* lb: best proven lower bound (separating axis v: v.w / |v|) */
     *deep = 0;
     int it = 0;
     for (; it < g_flags.gjk_max_iter; it++) {
@@ -349,6 +374,7 @@ static double gjk_core_distance(const shape_t *A, const shape_t *B, int *deep, i
         double nv[3] = {-v[0], -v[1], -v[2]};
         support(A, nv, sa); support(B, v, sb); sub3(sa, sb, w);
         double delta = dot3(v, w);
+        if (delta > 0 && delta / sqrt(vv) > lb) lb = delta / sqrt(vv);
         if (vv - delta <= g_flags.gjk_rel_tol * vv) break;            /* lower bound met */
         int dup = 0;
         for (int i = 0; i < n; i++) {
@@ -358,7 +384,10 @@ static double gjk_core_distance(const shape_t *A, const shape_t *B, int *deep, i
         if (dup) break;
         memcpy(W[n], w, sizeof(w)); n++;
         double vnew[3];
-        if (closest_simplex(W, &n, vnew)) { *deep = 1; vv = 0; break; }
+        if (closest_simplex(W, &n, vnew)) {
+            if (lb > 1e-9) break;          /* a separating axis exists: the enclosure is round-off */
+            *deep = 1; vv = 0; break;
+        }
         double vvn = dot3(vnew, vnew);
         if (vvn >= vv) break;                                          /* no progress (round-off) */
         memcpy(v, vnew, sizeof(v)); vv = vvn;
@@ -397,7 +426,13 @@ static void make_table(shape_t *s) { make_box(s, 0.5, 0.0, -0.12 - 0.46, 0.55, 0
 static void make_track(shape_t *s) { make_box(s, 0.0, 0.0, -0.06, 0.1, 0.55, 0.06); }
 
 /* obstacle: cylinder radius 0.05, height 0.4, axis = local z    reach.py:279-283,427-431,626-630 */
+static const double g_obst_cap_verts[6] = {0, 0, -0.2, 0, 0, 0.2};
 static void make_obstacle(const orc_scene_t *sc, shape_t *s) {
+    if (sc->geom == ORC_GEOM_CAPSULE) {
+        s->type = SH_HULL; s->verts = g_obst_cap_verts; s->nverts = 2; s->margin = 0.05;
+        quat_to_mat(sc->obs_quat, s->R); memcpy(s->t, sc->obs_pos, 3 * sizeof(double));
+        return;
+    }
     double m = prim_margin(0.05, 0.05, 0.2);
     s->type = SH_CYLZ; s->margin = m;
     s->he[0] = 0.05 - m; s->he[1] = 0.05 - m; s->he[2] = 0.2 - m;
@@ -405,6 +440,13 @@ static void make_obstacle(const orc_scene_t *sc, shape_t *s) {
 }
 
 static void make_target(const orc_scene_t *sc, shape_t *s) {
+    if (sc->geom == ORC_GEOM_CAPSULE) {
+        static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        s->type = SH_POINT; memcpy(s->R, I, sizeof(I));
+        s->margin = sc->tgt_type == 1 ? 0.02 : 0.025 * sqrt(3.0);
+        memcpy(s->t, sc->tgt_pos, 3 * sizeof(double));
+        return;
+    }
     if (sc->tgt_type == 1) {               /* sphere radius 0.02: point core, margin = radius  reach.py:270-277 */
         static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         s->type = SH_POINT; s->margin = 0.02; memcpy(s->R, I, sizeof(I));
@@ -429,7 +471,7 @@ static void make_link(const orc_scene_t *sc, int link, double pos[7][3], double 
                 }
             g_cap_init = 1;
         }
-        s->verts = g_cap_verts[link]; s->nverts = 2; s->margin = UR5E_CAPSULE_R[link];
+        s->verts = g_cap_verts[link]; s->nverts = 2; s->margin = UR5E_CAPSULE_R[link] + g_flags.hull_margin;
     } else {
         s->verts = &UR5E_HULL_VERTS[3 * UR5E_HULL_OFFSET[link]];
         s->nverts = UR5E_HULL_OFFSET[link + 1] - UR5E_HULL_OFFSET[link];

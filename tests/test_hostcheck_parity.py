@@ -1,0 +1,57 @@
+"""CPU tier: the product's own per-env FP32 arithmetic (urgym_env.cuh compiled for the host by tests/hostcheck)
+against the FP64 oracle, all four tasks, capsule and hull geometry, with auto-reset through the shared
+counter-based reset stream.  The CUDA kernels run exactly these functions, one env per thread (checked on the GPU
+by test_gpu_parity.py)."""
+import numpy as np
+import pytest
+
+from tests._hostcheck import HostCheckSim, ee_pose, philox
+from tests._parity import run_parity
+from oracle import oracle_env as oe
+
+TASKS = ["UR5OriReach-v1", "UR5ObsReach-v1", "UR5StaReach-v1", "UR5DynReach-v1"]
+
+
+def test_philox_matches_oracle_and_known_answer():
+    # Random123 known-answer vectors for philox4x32-10
+    assert philox((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert philox((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert philox((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        c = tuple(int(x) for x in rng.integers(0, 2 ** 32, 4)); k = tuple(int(x) for x in rng.integers(0, 2 ** 32, 2))
+        assert philox(c, k) == oe.philox4x32_10(c, k)
+
+
+def test_fk_pose_tolerance():
+    rng = np.random.default_rng(1)
+    q = np.concatenate([[[0, -1.5708, 0, -1.5708, 0, 0]], rng.uniform(-2 * np.pi, 2 * np.pi, (2000, 6))]).astype(np.float32)
+    ee = ee_pose(q)
+    sim = oe.OracleSim()
+    worst_p = worst_a = 0.0
+    for i in range(len(q)):
+        sim.set_joint_angles(q[i].astype(np.float64))
+        p, e = sim.get_link_position(7), sim.get_link_orientation(7)
+        if abs(abs(e[1]) - np.pi / 2) < 2e-2:       # Euler angles are ill-conditioned next to gimbal lock
+            continue
+        worst_p = max(worst_p, np.abs(ee[i, :3] - p).max())
+        d = np.abs(ee[i, 3:] - e) % (2 * np.pi)
+        worst_a = max(worst_a, np.minimum(d, 2 * np.pi - d).max())
+    assert worst_p < 1e-5 and worst_a < 1e-5, (worst_p, worst_a)
+
+
+@pytest.mark.parametrize("env_id", TASKS)
+def test_capsule_rollout_parity(env_id):
+    n, steps = 48, 70
+    sim = HostCheckSim(env_id, oe.GEOM_CAPSULE, n, seed=1234)
+    st = run_parity(sim, env_id, oe.GEOM_CAPSULE, n, steps, seed=1234)
+    assert st["steps"] > 0.9 * n * steps and st["resets"] > 0, st
+
+
+@pytest.mark.parametrize("env_id", TASKS)
+def test_hull_rollout_parity(env_id):
+    n, steps = 16, 40
+    sim = HostCheckSim(env_id, oe.GEOM_HULL, n, seed=99, offset=1000)
+    st = run_parity(sim, env_id, oe.GEOM_HULL, n, steps, seed=99, offset=1000, ld_tol=5e-5, rew_atol=1e-2)
+    assert st["steps"] > 0.9 * n * steps, st

@@ -1,0 +1,394 @@
+// urgym_api.cu -- the C ABI declared in include/urgym_b200.h: handle, state pool, dispatch to the per-(task,
+// geometry) kernel instantiations, state field access, statistics, host-buffer entry points.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+#include "urgym_kernels.cuh"
+#include "urgym_model.h"
+
+// ------------------------------------------------------------------------------------------------ field access
+// API layout (row-major [N,K], what the reference's numpy arrays look like) <-> planes
+struct FieldArgs {
+    StateView st;
+    int64_t n;
+    int field, task;
+    void *ext;      // device pointer in API layout
+    int to_state;   // 1: ext -> planes (set_state), 0: planes -> ext (get_state)
+};
+
+__device__ __forceinline__ float *e_word(const StateView &st, int task, int64_t i, int w) {
+    const int EW = task == TASK_ORI ? 6 : (task == TASK_OBS ? 9 : (task == TASK_STA ? 12 : 18));
+    const int NF = EW / 4;
+    if (w < 4 * NF) return reinterpret_cast<float *>(&st.e4[w / 4][i]) + (w % 4);
+    if (EW % 4 == 2) return reinterpret_cast<float *>(&st.e2[i]) + (w - 4 * NF);
+    return &st.e1[i];
+}
+
+__global__ void __launch_bounds__(URGYM_BLOCK) urgym_field_kernel(const FieldArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * URGYM_BLOCK + threadIdx.x;
+    if (i >= A.n) return;
+    float *qa = reinterpret_cast<float *>(&A.st.qa[i]), *qb = reinterpret_cast<float *>(&A.st.qb[i]);
+    float *x = reinterpret_cast<float *>(A.ext);
+    auto mv = [&](float *plane, float *e) { if (A.to_state) *plane = *e; else *e = *plane; };
+    switch (A.field) {
+    case URGYM_F_Q:
+        for (int k = 0; k < 4; k++) mv(qa + k, x + i * 6 + k);
+        for (int k = 0; k < 2; k++) mv(qb + k, x + i * 6 + 4 + k);
+        break;
+    case URGYM_F_ELAPSED: mv(qb + 2, x + i); break;            // int32 bit pattern
+    case URGYM_F_EP_RETURN: mv(qb + 3, x + i); break;
+    case URGYM_F_GOAL: {
+        const int G = A.task == TASK_OBS ? 3 : 6;
+        for (int k = 0; k < G; k++) mv(e_word(A.st, A.task, i, k), x + i * G + k);
+        break;
+    }
+    case URGYM_F_OBSTACLE: {
+        const int off = A.task == TASK_OBS ? 3 : 6;
+        for (int k = 0; k < 6; k++) mv(e_word(A.st, A.task, i, off + k), x + i * 6 + k);
+        break;
+    }
+    case URGYM_F_OBSTACLE_END:
+        for (int k = 0; k < 6; k++) mv(e_word(A.st, A.task, i, 12 + k), x + i * 6 + k);
+        break;
+    case URGYM_F_LINK_DIST: {
+        float *l = reinterpret_cast<float *>(&A.st.ld4[i]);
+        for (int k = 0; k < 4; k++) mv(l + k, x + i * 5 + k);
+        mv(&A.st.ld1[i], x + i * 5 + 4);
+        break;
+    }
+    case URGYM_F_VELOCITY: {
+        float *a = reinterpret_cast<float *>(&A.st.va[i]), *b = reinterpret_cast<float *>(&A.st.vb[i]);
+        for (int k = 0; k < 4; k++) mv(a + k, x + i * 6 + k);
+        for (int k = 0; k < 2; k++) mv(b + k, x + i * 6 + 4 + k);
+        break;
+    }
+    default: break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct urgym_env {
+    int task, geom, device;
+    int64_t n, offset;
+    uint64_t seed;
+    uint32_t event;         // reset-event counter: position of the counter-based reset stream
+    int autoreset;
+    StateView st;
+    ModelConst model;
+    void *pool;
+    unsigned long long *stats;
+    float4 *hull;
+    int64_t launches;
+    // staging for the host-buffer entry points
+    cudaStream_t hstream;
+    void *dstage;
+    size_t dstage_bytes;
+    char err[512];
+};
+
+static char g_create_err[512] = "";
+
+static int fail(urgym_env *h, int code, const char *fmt, const char *detail) {
+    char *dst = h ? h->err : g_create_err;
+    snprintf(dst, 512, fmt, detail ? detail : "");
+    return code;
+}
+#define CK(call)                                                                   \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) return fail(h, URGYM_ECUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+static int obs_dim(int task) { return task == 0 ? 18 : task == 1 ? 26 : task == 2 ? 29 : task == 3 ? 35 : -1; }
+static int goal_dim(int task) { return task == 1 ? 3 : (task >= 0 && task <= 3 ? 6 : -1); }
+
+extern "C" int urgym_obs_dim(int task) { return obs_dim(task); }
+extern "C" int urgym_goal_dim(int task) { return goal_dim(task); }
+extern "C" int64_t urgym_num_envs(const urgym_env_t *h) { return h ? h->n : 0; }
+extern "C" const char *urgym_last_error(const urgym_env_t *h) { return h ? h->err : g_create_err; }
+extern "C" int64_t urgym_launch_count(const urgym_env_t *h) { return h ? h->launches : 0; }
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_envs, int64_t env_index_offset,
+                            uint64_t seed, int device) {
+    urgym_env *h = nullptr;
+    if (!out) return fail(nullptr, URGYM_EINVAL, "urgym_create: out is NULL%s", "");
+    *out = nullptr;
+    if (task < 0 || task > 3) return fail(nullptr, URGYM_EINVAL, "urgym_create: task must be 0..3%s", "");
+    if (geom != URGYM_GEOM_HULL && geom != URGYM_GEOM_CAPSULE) return fail(nullptr, URGYM_EINVAL, "urgym_create: bad geom%s", "");
+    if (n_envs <= 0 || env_index_offset < 0) return fail(nullptr, URGYM_EINVAL, "urgym_create: n_envs must be > 0 and offset >= 0%s", "");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, URGYM_ENODEVICE, "urgym_create: no CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, URGYM_EINVAL, "urgym_create: device index out of range%s", "");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, URGYM_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, URGYM_ENODEVICE, "urgym_create: device is not sm_100 (built for sm_100a only)%s", "");
+    h = new (std::nothrow) urgym_env();
+    if (!h) return fail(nullptr, URGYM_ENOMEM, "urgym_create: host allocation failed%s", "");
+    memset(h, 0, sizeof(*h));
+    h->task = task; h->geom = geom; h->device = device; h->n = n_envs; h->offset = env_index_offset; h->seed = seed;
+    h->autoreset = 1;
+    int rc = URGYM_OK;
+    do {
+        if ((e = cudaSetDevice(device)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
+        build_model_const(h->model);
+        // planes: 16-byte groups first, all 256-byte aligned
+        const size_t n = (size_t)n_envs;
+        const size_t p16 = align_up(n * 16, 256), p8 = align_up(n * 8, 256), p4 = align_up(n * 4, 256);
+        const size_t total = 3 * p16 + p4 + 4 * p16 + p8 + p4 + p16 + p8 + URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8;
+        if ((e = cudaMalloc(&h->pool, total)) != cudaSuccess) { rc = URGYM_ENOMEM; break; }
+        if ((e = cudaMemset(h->pool, 0, total)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
+        char *p = (char *)h->pool;
+        h->st.qa = (float4 *)p; p += p16;
+        h->st.qb = (float4 *)p; p += p16;
+        h->st.ld4 = (float4 *)p; p += p16;
+        h->st.ld1 = (float *)p; p += p4;
+        for (int g = 0; g < 4; g++) { h->st.e4[g] = (float4 *)p; p += p16; }
+        h->st.e2 = (float2 *)p; p += p8;
+        h->st.e1 = (float *)p; p += p4;
+        h->st.va = (float4 *)p; p += p16;
+        h->st.vb = (float2 *)p; p += p8;
+        h->stats = (unsigned long long *)p;
+        if (geom == URGYM_GEOM_HULL) {
+            static float4 hv[UR5E_NUM_HULL_VERTS];
+            for (int i = 0; i < UR5E_NUM_HULL_VERTS; i++)
+                hv[i] = make_float4((float)UR5E_HULL_VERTS[3 * i], (float)UR5E_HULL_VERTS[3 * i + 1], (float)UR5E_HULL_VERTS[3 * i + 2], 0.0f);
+            if ((e = cudaMalloc(&h->hull, sizeof(hv))) != cudaSuccess) { rc = URGYM_ENOMEM; break; }
+            if ((e = cudaMemcpy(h->hull, hv, sizeof(hv), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
+        }
+        if ((e = cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
+    } while (0);
+    if (rc != URGYM_OK) {
+        fail(nullptr, rc, "urgym_create: %s", cudaGetErrorString(e));
+        if (h->hull) cudaFree(h->hull);
+        if (h->pool) cudaFree(h->pool);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return URGYM_OK;
+}
+
+extern "C" int urgym_destroy(urgym_env_t *h) {
+    if (!h) return URGYM_EINVAL;
+    cudaSetDevice(h->device);
+    if (h->hstream) cudaStreamDestroy(h->hstream);
+    if (h->dstage) cudaFree(h->dstage);
+    if (h->hull) cudaFree(h->hull);
+    if (h->pool) cudaFree(h->pool);
+    delete h;
+    return URGYM_OK;
+}
+
+extern "C" int urgym_set_autoreset(urgym_env_t *h, int enabled) {
+    if (!h) return URGYM_EINVAL;
+    h->autoreset = enabled ? 1 : 0;
+    return URGYM_OK;
+}
+extern "C" int urgym_get_event(const urgym_env_t *h, uint32_t *event) {
+    if (!h || !event) return URGYM_EINVAL;
+    *event = h->event;
+    return URGYM_OK;
+}
+extern "C" int urgym_set_event(urgym_env_t *h, uint32_t event) {
+    if (!h) return URGYM_EINVAL;
+    h->event = event;
+    return URGYM_OK;
+}
+
+static inline uint2 key_of(uint64_t seed) { return make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)); }
+
+// [geom][task]
+static const step_launcher_t k_step[2][4] = {
+    {urgym_inst_step_0_0, urgym_inst_step_1_0, urgym_inst_step_2_0, urgym_inst_step_3_0},
+    {urgym_inst_step_0_1, urgym_inst_step_1_1, urgym_inst_step_2_1, urgym_inst_step_3_1}};
+static const aux_launcher_t k_reset[2][4] = {
+    {urgym_inst_reset_0_0, urgym_inst_reset_1_0, urgym_inst_reset_2_0, urgym_inst_reset_3_0},
+    {urgym_inst_reset_0_1, urgym_inst_reset_1_1, urgym_inst_reset_2_1, urgym_inst_reset_3_1}};
+static const aux_launcher_t k_refresh[2][4] = {
+    {urgym_inst_refresh_0_0, urgym_inst_refresh_1_0, urgym_inst_refresh_2_0, urgym_inst_refresh_3_0},
+    {urgym_inst_refresh_0_1, urgym_inst_refresh_1_1, urgym_inst_refresh_2_1, urgym_inst_refresh_3_1}};
+static const aux_launcher_t k_observe[4] = {launch_observe<0>, launch_observe<1>, launch_observe<2>, launch_observe<3>};
+
+extern "C" int urgym_step(urgym_env_t *h, const float *actions, float *obs, float *achieved, float *desired,
+                          float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
+                          float *terminal_obs, float *terminal_achieved, void *stream) {
+    if (!h) return URGYM_EINVAL;
+    if (!actions || !obs || !reward || !terminated || !truncated || !is_success)
+        return fail(h, URGYM_EINVAL, "urgym_step: actions, obs, reward, terminated, truncated, is_success must not be NULL%s", "");
+    CK(cudaSetDevice(h->device));
+    StepArgs A;
+    A.st = h->st; A.n = h->n; A.offset = h->offset; A.key = key_of(h->seed);
+    A.event = ++h->event;
+    A.autoreset = h->autoreset;
+    A.actions = actions; A.obs = obs; A.ach = achieved; A.des = desired; A.rew = reward;
+    A.term = terminated; A.trunc = truncated; A.succ = is_success; A.tobs = terminal_obs; A.tach = terminal_achieved;
+    A.stats = h->stats; A.hull = h->hull;
+    CK(k_step[h->geom][h->task](h->model, A, (cudaStream_t)stream));
+    h->launches++;
+    return URGYM_OK;
+}
+
+extern "C" int urgym_reset(urgym_env_t *h, const uint8_t *mask, float *obs, float *achieved, float *desired, void *stream) {
+    if (!h) return URGYM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    AuxArgs A;
+    memset(&A, 0, sizeof(A));
+    A.st = h->st; A.n = h->n; A.offset = h->offset; A.key = key_of(h->seed);
+    A.event = ++h->event;
+    A.mask = mask; A.obs = obs; A.ach = achieved; A.des = desired; A.stats = h->stats; A.hull = h->hull;
+    CK(k_reset[h->geom][h->task](h->model, A, (cudaStream_t)stream));
+    h->launches++;
+    return URGYM_OK;
+}
+
+extern "C" int urgym_observe(urgym_env_t *h, float *obs, float *achieved, float *desired, void *stream) {
+    if (!h) return URGYM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    AuxArgs A;
+    memset(&A, 0, sizeof(A));
+    A.st = h->st; A.n = h->n; A.offset = h->offset; A.obs = obs; A.ach = achieved; A.des = desired;
+    CK(k_observe[h->task](h->model, A, (cudaStream_t)stream));
+    h->launches++;
+    return URGYM_OK;
+}
+
+extern "C" int urgym_refresh(urgym_env_t *h, uint8_t *collision, void *stream) {
+    if (!h) return URGYM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    AuxArgs A;
+    memset(&A, 0, sizeof(A));
+    A.st = h->st; A.n = h->n; A.offset = h->offset; A.collision = collision; A.hull = h->hull;
+    CK(k_refresh[h->geom][h->task](h->model, A, (cudaStream_t)stream));
+    h->launches++;
+    return URGYM_OK;
+}
+
+static int field_ok(urgym_env *h, int field) {
+    if (field < 0 || field >= URGYM_F_COUNT) return 0;
+    if (field == URGYM_F_OBSTACLE && h->task == 0) return 0;
+    if (field == URGYM_F_LINK_DIST && h->task == 0) return 0;
+    if ((field == URGYM_F_OBSTACLE_END || field == URGYM_F_VELOCITY) && h->task != 3) return 0;
+    return 1;
+}
+static int field_io(urgym_env *h, int field, void *ext, int to_state, void *stream) {
+    if (!h) return URGYM_EINVAL;
+    if (!ext) return fail(h, URGYM_EINVAL, "urgym_get/set_state: NULL pointer%s", "");
+    if (!field_ok(h, field)) return fail(h, URGYM_EUNSUPPORTED, "urgym_get/set_state: field not available for this task%s", "");
+    CK(cudaSetDevice(h->device));
+    FieldArgs A;
+    A.st = h->st; A.n = h->n; A.field = field; A.task = h->task; A.ext = ext; A.to_state = to_state;
+    urgym_field_kernel<<<grid_for(h->n), URGYM_BLOCK, 0, (cudaStream_t)stream>>>(A);
+    CK(cudaGetLastError());
+    h->launches++;
+    return URGYM_OK;
+}
+extern "C" int urgym_get_state(urgym_env_t *h, int field, void *dst, void *stream) { return field_io(h, field, dst, 0, stream); }
+extern "C" int urgym_set_state(urgym_env_t *h, int field, const void *src, void *stream) {
+    return field_io(h, field, const_cast<void *>(src), 1, stream);
+}
+
+extern "C" int urgym_stats(urgym_env_t *h, double out[URGYM_STATS_COUNT], int reset_after, void *stream) {
+    if (!h || !out) return URGYM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    unsigned long long host[URGYM_STAT_SLOTS * URGYM_STATS_COUNT];
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(host, h->stats, sizeof(host), cudaMemcpyDeviceToHost, s));
+    if (reset_after) CK(cudaMemsetAsync(h->stats, 0, sizeof(host), s));
+    CK(cudaStreamSynchronize(s));
+    unsigned long long sum[URGYM_STATS_COUNT] = {0};
+    for (int b = 0; b < URGYM_STAT_SLOTS; b++)
+        for (int k = 0; k < URGYM_STATS_COUNT; k++) sum[k] += host[b * URGYM_STATS_COUNT + k];
+    for (int k = 0; k < URGYM_STATS_COUNT; k++) out[k] = (double)sum[k];
+    out[1] = (double)(long long)sum[1] / (double)URGYM_RETURN_SCALE;
+    return URGYM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer entry points
+static int ensure_stage(urgym_env *h, size_t bytes) {
+    if (h->dstage_bytes >= bytes) return URGYM_OK;
+    if (h->dstage) { cudaFree(h->dstage); h->dstage = nullptr; h->dstage_bytes = 0; }
+    CK(cudaMalloc(&h->dstage, bytes));
+    h->dstage_bytes = bytes;
+    return URGYM_OK;
+}
+
+extern "C" int urgym_step_host(urgym_env_t *h, const float *actions, float *obs, float *achieved, float *desired,
+                               float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
+                               float *terminal_obs, float *terminal_achieved) {
+    if (!h) return URGYM_EINVAL;
+    if (!actions || !obs || !reward || !terminated || !truncated || !is_success)
+        return fail(h, URGYM_EINVAL, "urgym_step_host: actions, obs, reward, terminated, truncated, is_success must not be NULL%s", "");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n, D = obs_dim(h->task), G = goal_dim(h->task);
+    const size_t b_act = align_up(n * 6 * 4, 256), b_obs = align_up(n * D * 4, 256), b_g = align_up(n * G * 4, 256),
+                 b_r = align_up(n * 4, 256), b_f = align_up(n, 256);
+    int rc = ensure_stage(h, b_act + 2 * b_obs + 3 * b_g + b_r + 3 * b_f);
+    if (rc != URGYM_OK) return rc;
+    char *p = (char *)h->dstage;
+    float *d_act = (float *)p; p += b_act;
+    float *d_obs = (float *)p; p += b_obs;
+    float *d_tobs = (float *)p; p += b_obs;
+    float *d_ach = (float *)p; p += b_g;
+    float *d_des = (float *)p; p += b_g;
+    float *d_tach = (float *)p; p += b_g;
+    float *d_rew = (float *)p; p += b_r;
+    uint8_t *d_term = (uint8_t *)p; p += b_f;
+    uint8_t *d_trunc = (uint8_t *)p; p += b_f;
+    uint8_t *d_succ = (uint8_t *)p; p += b_f;
+    cudaStream_t s = h->hstream;
+    CK(cudaMemcpyAsync(d_act, actions, n * 6 * 4, cudaMemcpyHostToDevice, s));
+    rc = urgym_step(h, d_act, d_obs, achieved ? d_ach : nullptr, desired ? d_des : nullptr, d_rew, d_term, d_trunc, d_succ,
+                    terminal_obs ? d_tobs : nullptr, terminal_achieved ? d_tach : nullptr, s);
+    if (rc != URGYM_OK) return rc;
+    CK(cudaMemcpyAsync(obs, d_obs, n * D * 4, cudaMemcpyDeviceToHost, s));
+    if (achieved) CK(cudaMemcpyAsync(achieved, d_ach, n * G * 4, cudaMemcpyDeviceToHost, s));
+    if (desired) CK(cudaMemcpyAsync(desired, d_des, n * G * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(reward, d_rew, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(terminated, d_term, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(truncated, d_trunc, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(is_success, d_succ, n, cudaMemcpyDeviceToHost, s));
+    // terminal rows are meaningful only where the env finished; the whole arrays are copied (rows of running envs
+    // keep whatever the staging buffer held)
+    if (terminal_obs) CK(cudaMemcpyAsync(terminal_obs, d_tobs, n * D * 4, cudaMemcpyDeviceToHost, s));
+    if (terminal_achieved) CK(cudaMemcpyAsync(terminal_achieved, d_tach, n * G * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return URGYM_OK;
+}
+
+extern "C" int urgym_reset_host(urgym_env_t *h, const uint8_t *mask, float *obs, float *achieved, float *desired) {
+    if (!h) return URGYM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n, D = obs_dim(h->task), G = goal_dim(h->task);
+    const size_t b_obs = align_up(n * D * 4, 256), b_g = align_up(n * G * 4, 256), b_f = align_up(n, 256);
+    int rc = ensure_stage(h, b_obs + 2 * b_g + b_f);
+    if (rc != URGYM_OK) return rc;
+    char *p = (char *)h->dstage;
+    float *d_obs = (float *)p; p += b_obs;
+    float *d_ach = (float *)p; p += b_g;
+    float *d_des = (float *)p; p += b_g;
+    uint8_t *d_mask = (uint8_t *)p;
+    cudaStream_t s = h->hstream;
+    if (mask) CK(cudaMemcpyAsync(d_mask, mask, n, cudaMemcpyHostToDevice, s));
+    if (mask && obs) {      // rows that are not reset must keep the caller's contents
+        CK(cudaMemcpyAsync(d_obs, obs, n * D * 4, cudaMemcpyHostToDevice, s));
+        if (achieved) CK(cudaMemcpyAsync(d_ach, achieved, n * G * 4, cudaMemcpyHostToDevice, s));
+        if (desired) CK(cudaMemcpyAsync(d_des, desired, n * G * 4, cudaMemcpyHostToDevice, s));
+    }
+    rc = urgym_reset(h, mask ? d_mask : nullptr, obs ? d_obs : nullptr, achieved ? d_ach : nullptr, desired ? d_des : nullptr, s);
+    if (rc != URGYM_OK) return rc;
+    if (obs) CK(cudaMemcpyAsync(obs, d_obs, n * D * 4, cudaMemcpyDeviceToHost, s));
+    if (achieved) CK(cudaMemcpyAsync(achieved, d_ach, n * G * 4, cudaMemcpyDeviceToHost, s));
+    if (desired) CK(cudaMemcpyAsync(desired, d_des, n * G * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return URGYM_OK;
+}

@@ -11,7 +11,13 @@
 // No tensor cores: the work is chains of 3x3 transforms and small convex-distance iterations, not a contraction.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+
+// Every function here is __host__ __device__: the product only ever runs them inside kernels; the host
+// instantiation exists so tests/hostcheck can unit-test the very same arithmetic against the oracle on a box
+// without a GPU (it is not linked into liburgym_b200.so's call paths -- there is no CPU fallback).
+#define URGYM_HD __host__ __device__ __forceinline__
 
 namespace urgym {
 
@@ -21,46 +27,48 @@ struct ModelConst {
     float joint_rot[6][9];      // Rz(y)Ry(p)Rx(r) of each joint origin, row-major
     float cap_p0[7][3];         // bounding capsule of each link hull, link frame
     float cap_p1[7][3];
-    float cap_r[7];
+    float cap_m[7];             // capsule margin = bounding radius + hull_margin (so capsule distance <= hull distance)
     int hull_off[8];            // vertex ranges of links 0..6 inside the packed float4 vertex array
     // margins of Bullet's GJK pair detector (distance = |core gap| - marginA - marginB)
     float hull_margin;          // URDF mesh links: 0.001
     float table_c[3], table_he[3], table_margin;   // core half extents (already shrunk by the margin)
     float track_c[3], track_he[3], track_margin;
-    float obst_r, obst_h, obst_margin;             // cylinder core radius / half height
-    float tgt_box_he, tgt_box_margin;              // Sta/Dyn target box core
+    float obst_r, obst_h, obst_margin;             // hull mode: cylinder core radius / half height, margin
+    float tgt_box_he, tgt_box_margin;              // hull mode: Sta/Dyn target box core
     float tgt_sphere_margin;                       // Obs target sphere: point core, margin = radius
-    // capsule geometry mode stand-ins
-    float obst_cap_h, obst_cap_r;                  // obstacle as a capsule: half length of the segment, radius
-    float tgt_cap_r;                               // target as a sphere
+    // capsule geometry mode stand-ins (bounding shapes of the reference's obstacle / target)
+    float obst_cap_h, obst_cap_m;                  // obstacle: segment half length, margin (= radius)
+    float tgt_cap_m[4];                            // target as a sphere, per task (Ori unused)
+    // the reset pose (UR5.py:262) is the same for every env: its FK is computed once on the host in double
+    float neutral_q[6];
+    float neutral_ee[6];                           // EE position + PyBullet Euler triple
+    float neutral_ca[7][3], neutral_cb[7][3];      // world capsule segments of links 0..6
+    float neutral_R[7][9], neutral_p[7][3];        // world link poses (hull mode)
 };
 
-extern __constant__ ModelConst c_model;
-
 #define URGYM_PI_F 3.14159265358979323846f
-#define URGYM_NEUTRAL_Q {0.0f, -1.5708f, 0.0f, -1.5708f, 0.0f, 0.0f}   /* UR5.py:262 */
 
 // ------------------------------------------------------------------------------------------------ float3 helpers
-__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
-__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
-__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
-__device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
-__device__ __forceinline__ float3 cross(float3 a, float3 b) {
+URGYM_HD float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+URGYM_HD float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+URGYM_HD float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+URGYM_HD float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+URGYM_HD float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+URGYM_HD float dot(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+URGYM_HD float3 cross(float3 a, float3 b) {
     return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+URGYM_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 struct Pose {           // world pose of a link frame
     float R[9];         // row-major
     float3 p;
 };
-__device__ __forceinline__ float3 rot(const float *R, float3 v) {
+URGYM_HD float3 rot(const float *R, float3 v) {
     return f3(fmaf(R[0], v.x, fmaf(R[1], v.y, R[2] * v.z)), fmaf(R[3], v.x, fmaf(R[4], v.y, R[5] * v.z)),
               fmaf(R[6], v.x, fmaf(R[7], v.y, R[8] * v.z)));
 }
-__device__ __forceinline__ float3 rotT(const float *R, float3 v) {
+URGYM_HD float3 rotT(const float *R, float3 v) {
     return f3(fmaf(R[0], v.x, fmaf(R[3], v.y, R[6] * v.z)), fmaf(R[1], v.x, fmaf(R[4], v.y, R[7] * v.z)),
               fmaf(R[2], v.x, fmaf(R[5], v.y, R[8] * v.z)));
 }
@@ -69,7 +77,7 @@ __device__ __forceinline__ float3 rotT(const float *R, float3 v) {
 struct Quat { float x, y, z, w; };
 
 // pybullet getQuaternionFromEuler(roll,pitch,yaw) = Rz(yaw)Ry(pitch)Rx(roll)          pyb_setup.py:152,313-314
-__device__ __forceinline__ Quat quat_from_euler(float roll, float pitch, float yaw) {
+URGYM_HD Quat quat_from_euler(float roll, float pitch, float yaw) {
     float sr, cr, sp, cp, sy, cy;
     sincosf(0.5f * roll, &sr, &cr);
     sincosf(0.5f * pitch, &sp, &cp);
@@ -81,7 +89,7 @@ __device__ __forceinline__ Quat quat_from_euler(float roll, float pitch, float y
     q.w = cr * cp * cy + sr * sp * sy;
     return q;
 }
-__device__ __forceinline__ Quat quat_mul(Quat a, Quat b) {
+URGYM_HD Quat quat_mul(Quat a, Quat b) {
     Quat o;
     o.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
     o.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
@@ -90,7 +98,7 @@ __device__ __forceinline__ Quat quat_mul(Quat a, Quat b) {
     return o;
 }
 // pybullet getEulerFromQuaternion -> (roll, pitch, yaw), gimbal branch at |sarg| >= 0.99999   pyb_setup.py:190,248
-__device__ __forceinline__ float3 euler_from_quat(Quat q) {
+URGYM_HD float3 euler_from_quat(Quat q) {
     float sqx = q.x * q.x, sqy = q.y * q.y, sqz = q.z * q.z, squ = q.w * q.w;
     float sarg = -2.0f * (q.x * q.z - q.w * q.y);
     float3 e;
@@ -99,14 +107,17 @@ __device__ __forceinline__ float3 euler_from_quat(Quat q) {
     } else if (sarg >= 0.99999f) {
         e.y = 0.5f * URGYM_PI_F; e.x = 0.0f; e.z = 2.0f * atan2f(-q.x, q.y);
     } else {
-        e.y = asinf(sarg);
-        e.x = atan2f(2.0f * (q.y * q.z + q.w * q.x), squ - sqx - sqy + sqz);
+        // pitch = asin(sarg), evaluated as atan2(sin, cos) with cos(pitch) = |(R21, R22)|: same angle, but not
+        // ill-conditioned in FP32 when |pitch| approaches 90 degrees
+        float r21 = 2.0f * (q.y * q.z + q.w * q.x), r22 = squ - sqx - sqy + sqz;
+        e.y = atan2f(sarg, sqrtf(r21 * r21 + r22 * r22));
+        e.x = atan2f(r21, r22);
         e.z = atan2f(2.0f * (q.x * q.y + q.w * q.z), squ + sqx - sqy - sqz);
     }
     return e;
 }
 // btMatrix3x3::getRotation
-__device__ __forceinline__ Quat quat_from_mat(const float *R) {
+URGYM_HD Quat quat_from_mat(const float *R) {
     Quat q;
     float tr = R[0] + R[4] + R[8];
     if (tr > 0.0f) {
@@ -131,12 +142,12 @@ __device__ __forceinline__ Quat quat_from_mat(const float *R) {
 // Euler triple of a rotation matrix with PyBullet's formula.  For a unit quaternion
 //   -2(xz-wy) = -R20,  2(yz+wx) = R21,  w2-x2-y2+z2 = R22,  2(xy+wz) = R10,  w2+x2-y2-z2 = R00
 // so the regular branch needs no quaternion; the (rare) gimbal branch goes through quat_from_mat.
-__device__ __forceinline__ float3 euler_from_mat(const float *R) {
+URGYM_HD float3 euler_from_mat(const float *R) {
     float sarg = -R[6];
     if (fabsf(sarg) >= 0.99999f) return euler_from_quat(quat_from_mat(R));
-    return f3(atan2f(R[7], R[8]), asinf(sarg), atan2f(R[3], R[0]));
+    return f3(atan2f(R[7], R[8]), atan2f(sarg, sqrtf(R[7] * R[7] + R[8] * R[8])), atan2f(R[3], R[0]));
 }
-__device__ __forceinline__ void mat_from_quat(Quat q, float *R) {
+URGYM_HD void mat_from_quat(Quat q, float *R) {
     float n = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w, s = 2.0f / n;
     R[0] = 1.0f - s * (q.y * q.y + q.z * q.z); R[1] = s * (q.x * q.y - q.w * q.z); R[2] = s * (q.x * q.z + q.w * q.y);
     R[3] = s * (q.x * q.y + q.w * q.z); R[4] = 1.0f - s * (q.x * q.x + q.z * q.z); R[5] = s * (q.y * q.z - q.w * q.x);
@@ -145,7 +156,7 @@ __device__ __forceinline__ void mat_from_quat(Quat q, float *R) {
 
 // scipy Rotation.from_euler('ZYX', e).as_quat(): R = Rz(e0)Ry(e1)Rx(e2)   utils.py:48-54 (quirk Q2: e is PyBullet's
 // (roll,pitch,yaw), so roll is used as the z angle -- replicated literally)
-__device__ __forceinline__ Quat quat_ZYX(float e0, float e1, float e2) {
+URGYM_HD Quat quat_ZYX(float e0, float e1, float e2) {
     float sz, cz, sy, cy, sx, cx;
     sincosf(0.5f * e0, &sz, &cz);
     sincosf(0.5f * e1, &sy, &cy);
@@ -159,7 +170,7 @@ __device__ __forceinline__ Quat quat_ZYX(float e0, float e1, float e2) {
 }
 // utils.py:34-69: 2*arccos(|<qa,qb>|).  Evaluated as 2*atan2(|vec(qa^-1 qb)|, |<qa,qb>|), the same angle but
 // well conditioned in FP32 near 0 (arccos near 1 would lose half the digits).
-__device__ __forceinline__ float angular_distance(Quat a, Quat b) {
+URGYM_HD float angular_distance(Quat a, Quat b) {
     float d = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
     float vx = a.w * b.x - a.x * b.w - a.y * b.z + a.z * b.y;
     float vy = a.w * b.y - a.y * b.w - a.z * b.x + a.x * b.z;
@@ -170,9 +181,9 @@ __device__ __forceinline__ float angular_distance(Quat a, Quat b) {
 // ------------------------------------------------------------------------------------------------ forward kinematics
 // advance the chain by joint j (0..5): pose of PyBullet link j+1 from the pose of link j
 //   T_{j+1} = T_j * Trans(xyz_j) * Rz(y)Ry(p)Rx(r) * Rz(q_j)                      ur5e.urdf:232-279
-__device__ __forceinline__ void fk_advance(Pose &T, int j, float qj) {
-    const float *X = c_model.joint_xyz[j];
-    const float *F = c_model.joint_rot[j];
+URGYM_HD void fk_advance(const ModelConst &M, Pose &T, int j, float qj) {
+    const float *X = M.joint_xyz[j];
+    const float *F = M.joint_rot[j];
     T.p = T.p + rot(T.R, f3(X[0], X[1], X[2]));
     float A[9];
 #pragma unroll
@@ -189,44 +200,58 @@ __device__ __forceinline__ void fk_advance(Pose &T, int j, float qj) {
         T.R[3 * r + 2] = A[3 * r + 2];
     }
 }
-__device__ __forceinline__ void pose_identity(Pose &T) {
+URGYM_HD void pose_identity(Pose &T) {
     T.R[0] = 1; T.R[1] = 0; T.R[2] = 0; T.R[3] = 0; T.R[4] = 1; T.R[5] = 0; T.R[6] = 0; T.R[7] = 0; T.R[8] = 1;
     T.p = f3(0, 0, 0);
 }
 // pose of link `link` (1..6)
-__device__ __forceinline__ void fk_link(const float *q, int link, Pose &T) {
+URGYM_HD void fk_link(const ModelConst &M, const float *q, int link, Pose &T) {
     pose_identity(T);
-    for (int j = 0; j < link; j++) fk_advance(T, j, q[j]);
+    for (int j = 0; j < link; j++) fk_advance(M, T, j, q[j]);
 }
 
 // ------------------------------------------------------------------------------------------------ Philox4x32-10
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+URGYM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+URGYM_HD float rsqrt_f(float x) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+URGYM_HD uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         if (r) { k.x += 0x9E3779B9u; k.y += 0xBB67AE85u; }
-        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
         c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
     }
     return c;
 }
-__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }   // 2^-24
+URGYM_HD float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }   // 2^-24
 
 struct ResetStream {        // counter = (iteration*blocks_per_iter + block, episode, env_lo, env_hi); key = seed
     uint2 key; uint32_t episode, env_lo, env_hi, bpi, iter;
-    __device__ __forceinline__ uint4 block(uint32_t b) const {
+    URGYM_HD uint4 block(uint32_t b) const {
         return philox4x32_10(make_uint4(iter * bpi + b, episode, env_lo, env_hi), key);
     }
 };
 
 // utils.py:81-86  sample_euler_constrained: deg2rad([U(-90,-180), 0, U(0,-180)]) with numpy's low+(high-low)*u
-__device__ __forceinline__ void euler_constrained(float u_roll, float u_yaw, float &roll, float &yaw) {
+URGYM_HD void euler_constrained(float u_roll, float u_yaw, float &roll, float &yaw) {
     const float D2R = URGYM_PI_F / 180.0f;
     roll = (-90.0f + -90.0f * u_roll) * D2R;
     yaw = (-180.0f * u_yaw) * D2R;
 }
 // utils.py:88-101  sample_euler_obstacle
-__device__ __forceinline__ void euler_obstacle(float u_sign, float u_roll, float u_pitch, float &roll, float &pitch) {
+URGYM_HD void euler_obstacle(float u_sign, float u_roll, float u_pitch, float &roll, float &pitch) {
     const float D2R = URGYM_PI_F / 180.0f;
     float r = (u_sign < 0.5f) ? (-30.0f + -120.0f * u_roll) : (30.0f + 120.0f * u_roll);
     float p = (r < -90.0f || r > 90.0f) ? (-30.0f + -120.0f * u_pitch) : (30.0f + 120.0f * u_pitch);
@@ -237,8 +262,8 @@ __device__ __forceinline__ void euler_obstacle(float u_sign, float u_roll, float
 // support points of the cores Bullet's GJK sees (btConvexShape::localGetSupportVertexWithoutMarginNonVirtual)
 struct HullW {                      // link hull: vertices in the link frame (shared memory), posed by T
     const float4 *v; int n; const Pose *T;
-    __device__ __forceinline__ float3 center() const { return T->p; }
-    __device__ __forceinline__ float3 support(float3 d) const {
+    URGYM_HD float3 center() const { return T->p; }
+    URGYM_HD float3 support(float3 d) const {
         float3 l = rotT(T->R, d);
         float best = -3.0e38f; int bi = 0;
 #pragma unroll 4
@@ -253,64 +278,69 @@ struct HullW {                      // link hull: vertices in the link frame (sh
 };
 struct SegW {                       // capsule core: a segment in world space
     float3 a, b;
-    __device__ __forceinline__ float3 center() const { return 0.5f * (a + b); }
-    __device__ __forceinline__ float3 support(float3 d) const { return dot(d, b - a) > 0.0f ? b : a; }
+    URGYM_HD float3 center() const { return 0.5f * (a + b); }
+    URGYM_HD float3 support(float3 d) const { return dot(d, b - a) > 0.0f ? b : a; }
 };
 struct CylW {                       // obstacle core: cylinder about unit axis u through c  (btCylinderShapeZ)
     float3 c, u; float r, h;
-    __device__ __forceinline__ float3 center() const { return c; }
-    __device__ __forceinline__ float3 support(float3 d) const {
+    URGYM_HD float3 center() const { return c; }
+    URGYM_HD float3 support(float3 d) const {
         float dz = dot(d, u);
         float3 dp = d - dz * u;
+        dp = dp - dot(dp, u) * u;       // second Gram-Schmidt pass: when d is nearly parallel to the axis the first
+                                        // difference is mostly round-off and would tilt the rim point off the cap
         float s2 = dot(dp, dp);
         float3 o = c + (dz < 0.0f ? -h : h) * u;
-        if (s2 > 0.0f) o = o + (r * rsqrtf(s2)) * dp;
+        if (s2 > 0.0f) o = o + (r * rsqrt_f(s2)) * dp;
         return o;
     }
 };
 struct BoxA {                       // axis-aligned box core (table, track)
     float3 c, he;
-    __device__ __forceinline__ float3 center() const { return c; }
-    __device__ __forceinline__ float3 support(float3 d) const {
+    URGYM_HD float3 center() const { return c; }
+    URGYM_HD float3 support(float3 d) const {
         return f3(c.x + (d.x >= 0.0f ? he.x : -he.x), c.y + (d.y >= 0.0f ? he.y : -he.y), c.z + (d.z >= 0.0f ? he.z : -he.z));
     }
 };
 struct BoxO {                       // oriented cube core (Sta/Dyn target)
     float3 c; float R[9]; float he;
-    __device__ __forceinline__ float3 center() const { return c; }
-    __device__ __forceinline__ float3 support(float3 d) const {
+    URGYM_HD float3 center() const { return c; }
+    URGYM_HD float3 support(float3 d) const {
         float3 l = rotT(R, d);
         return c + rot(R, f3(l.x >= 0.0f ? he : -he, l.y >= 0.0f ? he : -he, l.z >= 0.0f ? he : -he));
     }
 };
 
-// closest point to the origin on triangle abc, barycentric weights (Ericson, RTCD 5.1.5)
-__device__ __forceinline__ void closest_tri(float3 a, float3 b, float3 c, float &la, float &lb, float &lc) {
-    float3 ab = b - a, ac = c - a;
-    float d1 = -dot(ab, a), d2 = -dot(ac, a);
-    if (d1 <= 0.0f && d2 <= 0.0f) { la = 1; lb = 0; lc = 0; return; }
-    float d3 = -dot(ab, b), d4 = -dot(ac, b);
-    if (d3 >= 0.0f && d4 <= d3) { la = 0; lb = 1; lc = 0; return; }
-    float vc = d1 * d4 - d3 * d2;
-    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) { float v = d1 / (d1 - d3); la = 1 - v; lb = v; lc = 0; return; }
-    float d5 = -dot(ab, c), d6 = -dot(ac, c);
-    if (d6 >= 0.0f && d5 <= d6) { la = 0; lb = 0; lc = 1; return; }
-    float vb = d5 * d2 - d1 * d6;
-    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) { float w = d2 / (d2 - d6); la = 1 - w; lb = 0; lc = w; return; }
-    float va = d3 * d6 - d5 * d4;
-    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
-        float w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); la = 0; lb = 1 - w; lc = w; return;
+// closest point to the origin on triangle abc, barycentric weights.  Interior solution from the 2x2 normal
+// equations; when it falls outside (or the triangle is degenerate) the best of the three edge projections.
+// Written for FP32 robustness rather than minimum flops: region classification by products of large dot products
+// (the classic formulation) stalls GJK when the simplex is small next to its distance from the origin.
+URGYM_HD void closest_tri(float3 a, float3 b, float3 c, float &la, float &lb, float &lc) {
+    float3 ab = b - a, ac = c - a, bc = c - b;
+    float s = -dot(a, ab), t = -dot(a, ac);
+    float E = dot(ab, ab), F = dot(ab, ac), G = dot(ac, ac);
+    float det = E * G - F * F;
+    if (det > 1e-10f * E * G) {
+        float u = s * G - t * F, v = t * E - s * F;
+        if (u >= 0.0f && v >= 0.0f && u + v <= det) {
+            float inv = 1.0f / det;
+            lb = u * inv; lc = v * inv; la = 1.0f - lb - lc;
+            return;
+        }
     }
-    float den = 1.0f / (va + vb + vc), v = vb * den, w = vc * den;
-    la = 1 - v - w; lb = v; lc = w;
-}
-__device__ __forceinline__ bool origin_outside(float3 a, float3 b, float3 c, float3 d) {
-    float3 n = cross(b - a, c - a);
-    return (-dot(a, n)) * dot(d - a, n) <= 0.0f;
+    float t1 = E > 0.0f ? clampf(s / E, 0.0f, 1.0f) : 0.0f;
+    float t2 = G > 0.0f ? clampf(t / G, 0.0f, 1.0f) : 0.0f;
+    float H = dot(bc, bc);
+    float t3 = H > 0.0f ? clampf(-dot(b, bc) / H, 0.0f, 1.0f) : 0.0f;
+    float3 x1 = a + t1 * ab, x2 = a + t2 * ac, x3 = b + t3 * bc;
+    float d1 = dot(x1, x1), d2 = dot(x2, x2), d3 = dot(x3, x3);
+    if (d1 <= d2 && d1 <= d3) { la = 1.0f - t1; lb = t1; lc = 0.0f; }
+    else if (d2 <= d3) { la = 1.0f - t2; lb = 0.0f; lc = t2; }
+    else { la = 0.0f; lb = 1.0f - t3; lc = t3; }
 }
 
 // Reduce the simplex to the sub-simplex supporting the point closest to the origin (v).  true = origin enclosed.
-__device__ __forceinline__ bool closest_simplex(float3 (&W)[4], int &n, float3 &v) {
+URGYM_HD bool closest_simplex(float3 (&W)[4], int &n, float3 &v) {
     float l[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (n == 1) {
         l[0] = 1.0f;
@@ -322,29 +352,39 @@ __device__ __forceinline__ bool closest_simplex(float3 (&W)[4], int &n, float3 &
     } else if (n == 3) {
         closest_tri(W[0], W[1], W[2], l[0], l[1], l[2]);
     } else {
-        float best = 3.0e38f; bool any = false;
+        // tetrahedron: barycentric coordinates of the origin from signed volumes.  The origin is enclosed only if
+        // all four are positive and the tetrahedron is not (numerically) flat; otherwise the closest point lies on
+        // a face whose opposite vertex has a non-positive coordinate.
+        float3 ad = W[0] - W[3], bd = W[1] - W[3], cd = W[2] - W[3], od = -W[3];
+        float det = dot(ad, cross(bd, cd));
+        float L2 = fmaxf(fmaxf(dot(ad, ad), dot(bd, bd)), dot(cd, cd));
+        bool flat = det * det <= 1e-10f * L2 * L2 * L2;
+        float la = dot(od, cross(bd, cd)), lb = dot(ad, cross(od, cd)), lc = dot(ad, cross(bd, od));
+        if (det < 0.0f) { la = -la; lb = -lb; lc = -lc; det = -det; }
+        float ld = det - la - lb - lc;
+        if (!flat && la > 0.0f && lb > 0.0f && lc > 0.0f && ld > 0.0f) return true;
+        float best = 3.0e38f;
         float a, b, c;
-        if (origin_outside(W[0], W[1], W[2], W[3])) {
+        if (flat || ld <= 0.0f) {       // face 0 1 2 (opposite vertex 3)
             closest_tri(W[0], W[1], W[2], a, b, c);
             float3 p = a * W[0] + b * W[1] + c * W[2]; float dd = dot(p, p);
-            if (dd < best) { best = dd; any = true; l[0] = a; l[1] = b; l[2] = c; l[3] = 0; }
+            if (dd < best) { best = dd; l[0] = a; l[1] = b; l[2] = c; l[3] = 0; }
         }
-        if (origin_outside(W[0], W[2], W[3], W[1])) {
+        if (flat || lb <= 0.0f) {       // face 0 2 3 (opposite vertex 1)
             closest_tri(W[0], W[2], W[3], a, b, c);
             float3 p = a * W[0] + b * W[2] + c * W[3]; float dd = dot(p, p);
-            if (dd < best) { best = dd; any = true; l[0] = a; l[1] = 0; l[2] = b; l[3] = c; }
+            if (dd < best) { best = dd; l[0] = a; l[1] = 0; l[2] = b; l[3] = c; }
         }
-        if (origin_outside(W[0], W[3], W[1], W[2])) {
+        if (flat || lc <= 0.0f) {       // face 0 3 1 (opposite vertex 2)
             closest_tri(W[0], W[3], W[1], a, b, c);
             float3 p = a * W[0] + b * W[3] + c * W[1]; float dd = dot(p, p);
-            if (dd < best) { best = dd; any = true; l[0] = a; l[1] = c; l[2] = 0; l[3] = b; }
+            if (dd < best) { best = dd; l[0] = a; l[1] = c; l[2] = 0; l[3] = b; }
         }
-        if (origin_outside(W[1], W[3], W[2], W[0])) {
+        if (flat || la <= 0.0f) {       // face 1 3 2 (opposite vertex 0)
             closest_tri(W[1], W[3], W[2], a, b, c);
             float3 p = a * W[1] + b * W[3] + c * W[2]; float dd = dot(p, p);
-            if (dd < best) { best = dd; any = true; l[0] = 0; l[1] = a; l[2] = c; l[3] = b; }
+            if (dd < best) { best = dd; l[0] = 0; l[1] = a; l[2] = c; l[3] = b; }
         }
-        if (!any) return true;
     }
     float3 nv = f3(0, 0, 0);
     float3 T[4];
@@ -366,12 +406,14 @@ __device__ __forceinline__ bool closest_simplex(float3 (&W)[4], int &n, float3 &
     return false;
 }
 
+#ifndef URGYM_GJK_MAX_ITER
 #define URGYM_GJK_MAX_ITER 48
+#endif
 #define URGYM_GJK_REL_TOL 1.0e-6f     /* Bullet's REL_ERROR2 on the squared distance (btGjkPairDetector) */
 
 // distance between the cores of A and B (0 and deep=true when they intersect)
 template <class SA, class SB>
-__device__ __forceinline__ float gjk_distance(const SA &A, const SB &B, bool &deep) {
+URGYM_HD float gjk_distance(const SA &A, const SB &B, bool &deep, float3 *v_out = nullptr) {
     float3 W[4];
     int n = 1;
     float3 d = A.center() - B.center();
@@ -379,11 +421,13 @@ __device__ __forceinline__ float gjk_distance(const SA &A, const SB &B, bool &de
     float3 v = A.support(-d) - B.support(d);
     W[0] = v;
     float vv = dot(v, v);
+    float lb = 0.0f;                    // best proven lower bound of the distance (separating-axis bound v.w / |v|)
     deep = false;
     for (int it = 0; it < URGYM_GJK_MAX_ITER; it++) {
         if (vv < 1e-14f) { deep = true; vv = 0.0f; break; }
         float3 w = A.support(-v) - B.support(v);
         float delta = dot(v, w);
+        if (delta > 0.0f) lb = fmaxf(lb, delta * rsqrt_f(vv));
         if (vv - delta <= URGYM_GJK_REL_TOL * vv) break;
         bool dup = false;
 #pragma unroll
@@ -393,17 +437,21 @@ __device__ __forceinline__ float gjk_distance(const SA &A, const SB &B, bool &de
         if (n == 1) W[1] = w; else if (n == 2) W[2] = w; else W[3] = w;
         n++;
         float3 vn;
-        if (closest_simplex(W, n, vn)) { deep = true; vv = 0.0f; break; }
+        if (closest_simplex(W, n, vn)) {
+            if (lb > 1e-5f) break;      // a separating axis was already found: the enclosure is round-off, keep v
+            deep = true; vv = 0.0f; break;
+        }
         float vvn = dot(vn, vn);
         if (vvn >= vv) break;
         v = vn; vv = vvn;
     }
+    if (v_out) *v_out = v;          // closest vector (from B to A) of the last iterate
     return sqrtf(vv);
 }
 
 // ------------------------------------------------------------------------------------------------ closed forms
 // squared distance between segments p1q1 and p2q2 (Ericson, RTCD 5.1.9)
-__device__ __forceinline__ float segseg_dist2(float3 p1, float3 q1, float3 p2, float3 q2) {
+URGYM_HD float segseg_dist2(float3 p1, float3 q1, float3 p2, float3 q2) {
     float3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
     float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
     float s, t;
@@ -425,20 +473,20 @@ __device__ __forceinline__ float segseg_dist2(float3 p1, float3 q1, float3 p2, f
     return dot(dd, dd);
 }
 // squared distance from point p to the axis-aligned box (c, he)
-__device__ __forceinline__ float point_box_dist2(float3 p, float3 c, float3 he) {
+URGYM_HD float point_box_dist2(float3 p, float3 c, float3 he) {
     float ex = fmaxf(fabsf(p.x - c.x) - he.x, 0.0f), ey = fmaxf(fabsf(p.y - c.y) - he.y, 0.0f),
           ez = fmaxf(fabsf(p.z - c.z) - he.z, 0.0f);
     return ex * ex + ey * ey + ez * ez;
 }
 // lower bound of the distance between segment ab and box (c, he): distance between their AABBs
-__device__ __forceinline__ float seg_box_lower2(float3 a, float3 b, float3 c, float3 he) {
+URGYM_HD float seg_box_lower2(float3 a, float3 b, float3 c, float3 he) {
     float gx = fmaxf(fmaxf(fminf(a.x, b.x) - (c.x + he.x), (c.x - he.x) - fmaxf(a.x, b.x)), 0.0f);
     float gy = fmaxf(fmaxf(fminf(a.y, b.y) - (c.y + he.y), (c.y - he.y) - fmaxf(a.y, b.y)), 0.0f);
     float gz = fmaxf(fmaxf(fminf(a.z, b.z) - (c.z + he.z), (c.z - he.z) - fmaxf(a.z, b.z)), 0.0f);
     return gx * gx + gy * gy + gz * gz;
 }
 // exact distance between segment ab and the box: f(t) = dist^2(a + t(b-a), box) is convex and C1; bisect f'.
-__device__ __forceinline__ float seg_box_dist(float3 a, float3 b, float3 c, float3 he) {
+URGYM_HD float seg_box_dist(float3 a, float3 b, float3 c, float3 he) {
     float3 d = b - a, a0 = a - c;
     float lo = 0.0f, hi = 1.0f;
     auto fprime = [&](float t) {
@@ -456,7 +504,7 @@ __device__ __forceinline__ float seg_box_dist(float3 a, float3 b, float3 c, floa
     return sqrtf(point_box_dist2(a + t * d, c, he));
 }
 // distance from point p to the cylinder core (c, unit axis u, r, h)
-__device__ __forceinline__ float point_cyl_dist(float3 p, const CylW &C) {
+URGYM_HD float point_cyl_dist(float3 p, const CylW &C) {
     float3 w = p - C.c;
     float z = dot(w, C.u);
     float3 pr = w - z * C.u;

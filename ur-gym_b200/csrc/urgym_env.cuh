@@ -1,0 +1,578 @@
+// urgym_env.cuh -- one environment's step / reset / observe, as the kernels run it (one env per thread).
+//
+// Reference semantics followed here (file:line relative to the UR-gym repository):
+//   RobotTaskEnv.step / reset / _get_obs        UR_gym/envs/core.py:252-273,303-317
+//   TimeLimit(max_episode_steps=100)            UR_gym/__init__.py:19-42
+//   UR5Ori.set_action / get_obs / reset         UR_gym/envs/robots/UR5.py:273-279,304-332
+//   ReachOri / ReachObs / ReachSta / ReachDyn   UR_gym/envs/tasks/reach.py:141-236,239-374,377-573,576-785
+//   PyBullet.check_collision / get_link_distances / get_target_to_obstacle_distance
+//                                               UR_gym/pyb_setup.py:382-456
+// State words per env ("episode constants" E are rewritten only at reset):
+//   q[6], elapsed (TimeLimit counter == ReachDyn.step_num), ep_return, link_dist[5] (== last_dist), E[EW]
+//   E: Ori goal[6] | Obs goal[3] obstacle[6] | Sta goal[6] obstacle[6] | Dyn goal[6] obstacle_start[6] obstacle_end[6]
+#pragma once
+#include "urgym_device.cuh"
+
+namespace urgym {
+
+enum { TASK_ORI = 0, TASK_OBS = 1, TASK_STA = 2, TASK_DYN = 3 };
+enum { GEOM_HULL = 0, GEOM_CAPSULE = 1 };
+
+#define URGYM_MAX_STEPS 100          /* UR_gym/__init__.py:22,28,34,41 */
+#define URGYM_MAX_RESET_ITERS 256    /* rejection loop bound; P(reached) ~ 0.83^256 */
+#define URGYM_COLLISION_MARGIN 0.01f /* getClosestPoints(distance=0.01)  pyb_setup.py:401,410,421 */
+#define URGYM_DT_ENV 0.04f           /* 20 substeps x 1/500 s            pyb_setup.py:25,40,50 */
+
+template <int TASK> struct Traits;
+template <> struct Traits<TASK_ORI> {
+    static constexpr int OBS = 18, GOAL = 6, EW = 6, BPI = 2, OBST = -1;
+    static constexpr bool HAS_OBST = false, ORI = true, DYN = false;
+};
+template <> struct Traits<TASK_OBS> {
+    static constexpr int OBS = 26, GOAL = 3, EW = 9, BPI = 3, OBST = 3;
+    static constexpr bool HAS_OBST = true, ORI = false, DYN = false;
+};
+template <> struct Traits<TASK_STA> {
+    static constexpr int OBS = 29, GOAL = 6, EW = 12, BPI = 3, OBST = 6;
+    static constexpr bool HAS_OBST = true, ORI = true, DYN = false;
+};
+template <> struct Traits<TASK_DYN> {
+    static constexpr int OBS = 35, GOAL = 6, EW = 18, BPI = 5, OBST = 6;   // OBST = obstacle_start; end = OBST + 6
+    static constexpr bool HAS_OBST = true, ORI = true, DYN = true;
+};
+
+// goal / obstacle sampling boxes   reach.py:151-152, 248-251, 385-388, 584-587
+template <int TASK> URGYM_HD void goal_range(float3 &lo, float3 &hi) {
+    if (TASK == TASK_OBS) { lo = f3(0.3f, -0.5f, -0.1f); hi = f3(0.75f, 0.5f, 0.2f); }
+    else if (TASK == TASK_DYN) { lo = f3(0.4f, -0.5f, 0.0f); hi = f3(0.75f, 0.5f, 0.2f); }
+    else { lo = f3(0.3f, -0.5f, 0.0f); hi = f3(0.75f, 0.5f, 0.2f); }
+}
+template <int TASK> URGYM_HD void obstacle_range(float3 &lo, float3 &hi) {
+    if (TASK == TASK_DYN) { lo = f3(0.5f, -0.8f, 0.25f); hi = f3(1.2f, 0.8f, 0.75f); }
+    else { lo = f3(0.5f, -0.5f, 0.25f); hi = f3(1.0f, 0.5f, 0.55f); }
+}
+
+struct EnvState {
+    float q[6];
+    int elapsed;
+    float ep_ret;
+    float ld[5];
+    float E[18];
+};
+
+struct StepOut {
+    float reward;
+    bool terminated, truncated, success, collision;
+};
+
+// ------------------------------------------------------------------------------------------------ obstacle pose
+struct ObstW {          // obstacle in the world: centre, orientation, unit axis (local z)
+    float3 c;
+    Quat q;
+    float3 u;
+};
+URGYM_HD float3 quat_axis_z(Quat q) {     // third column of the rotation matrix of a unit quaternion
+    return f3(2.0f * (q.x * q.z + q.w * q.y), 2.0f * (q.y * q.z - q.w * q.x), 1.0f - 2.0f * (q.x * q.x + q.y * q.y));
+}
+URGYM_HD ObstW obstacle_static(const float *o) {      // set_base_pose(position, euler)   pyb_setup.py:305-317
+    ObstW O;
+    O.c = f3(o[0], o[1], o[2]);
+    O.q = quat_from_euler(o[3], o[4], o[5]);
+    O.u = quat_axis_z(O.q);
+    return O;
+}
+// ReachDyn.set_velocity (reach.py:728-753) + the kinematic motion of a mass-0 base under resetBaseVelocity over
+// the substeps (pyb_setup.py:52-55,340-349).  The twist is constant while step_num < 25, so the pose after `moved`
+// env steps is closed form: translation moved*0.04*v, rotation by moved*0.04*|w| about w (Bullet composes one fixed
+// world-frame increment per substep).  vel = [v, w] as ReachDyn.velocity holds it.
+URGYM_HD void dyn_twist(const float *start, const float *end, float *vel, Quat &qs, float3 &axis, float &angle) {
+    qs = quat_from_euler(start[3], start[4], start[5]);
+    Quat qe = quat_from_euler(end[3], end[4], end[5]);
+    // getDifferenceQuaternion(start, end) = nearest(end) * start^-1                  pyb_setup.py:351-359
+    float dm = (qs.x - qe.x) * (qs.x - qe.x) + (qs.y - qe.y) * (qs.y - qe.y) + (qs.z - qe.z) * (qs.z - qe.z) +
+               (qs.w - qe.w) * (qs.w - qe.w);
+    float dp = (qs.x + qe.x) * (qs.x + qe.x) + (qs.y + qe.y) * (qs.y + qe.y) + (qs.z + qe.z) * (qs.z + qe.z) +
+               (qs.w + qe.w) * (qs.w + qe.w);
+    if (!(dm < dp)) { qe.x = -qe.x; qe.y = -qe.y; qe.z = -qe.z; qe.w = -qe.w; }
+    Quat si; si.x = -qs.x; si.y = -qs.y; si.z = -qs.z; si.w = qs.w;
+    Quat d = quat_mul(qe, si);
+    // getAxisAngleFromQuaternion: angle = 2 acos(w), axis = xyz / sqrt(1 - w^2), (1,0,0) if degenerate  pyb_setup.py:361-363
+    float w = clampf(d.w, -1.0f, 1.0f);
+    float s2 = 1.0f - d.w * d.w;
+    float vn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);      // = sqrt(1 - w^2) for a unit quaternion, better conditioned
+    angle = 2.0f * atan2f(vn, w);                             // = 2 acos(w)
+    if (s2 < 10.0f * 1.1920929e-7f || vn == 0.0f) axis = f3(1.0f, 0.0f, 0.0f);
+    else axis = (1.0f / vn) * f3(d.x, d.y, d.z);
+    vel[0] = (end[0] - start[0]) * 0.5f; vel[1] = (end[1] - start[1]) * 0.5f; vel[2] = (end[2] - start[2]) * 0.5f;
+    vel[3] = axis.x * angle * 0.5f; vel[4] = axis.y * angle * 0.5f; vel[5] = axis.z * angle * 0.5f;
+}
+URGYM_HD ObstW obstacle_dyn(const float *start, const float *vel, Quat qs, float3 axis, float angle, int moved) {
+    ObstW O;
+    float t = (float)moved * URGYM_DT_ENV;
+    O.c = f3(start[0] + t * vel[0], start[1] + t * vel[1], start[2] + t * vel[2]);
+    float s, c;
+    sincosf(0.25f * t * angle, &s, &c);          // half of the rotated angle t * (angle / 2)
+    Quat r; r.x = axis.x * s; r.y = axis.y * s; r.z = axis.z * s; r.w = c;
+    O.q = quat_mul(r, qs);                        // world-frame increment on the left
+    O.u = quat_axis_z(O.q);
+    return O;
+}
+
+// ------------------------------------------------------------------------------------------------ robot geometry
+// exact squared distance between segment ab and the axis-aligned box (c, he).  g(t) = 1/2 d/dt dist^2 is monotone
+// and piecewise linear with breakpoints where the point crosses a slab face; bracket the root between breakpoints.
+URGYM_HD float seg_box_dist2(float3 a, float3 b, float3 c, float3 he) {
+    float3 p0 = a - c, d = b - a;
+    auto ex = [](float p, float h) { return p - clampf(p, -h, h); };
+    auto g = [&](float t) {
+        return ex(fmaf(t, d.x, p0.x), he.x) * d.x + ex(fmaf(t, d.y, p0.y), he.y) * d.y + ex(fmaf(t, d.z, p0.z), he.z) * d.z;
+    };
+    auto d2 = [&](float t) {
+        float x = ex(fmaf(t, d.x, p0.x), he.x), y = ex(fmaf(t, d.y, p0.y), he.y), z = ex(fmaf(t, d.z, p0.z), he.z);
+        return x * x + y * y + z * z;
+    };
+    float lo = 0.0f, hi = 1.0f, glo = g(0.0f), ghi = g(1.0f);
+    if (glo >= 0.0f) return d2(0.0f);
+    if (ghi <= 0.0f) return d2(1.0f);
+    const float pp[3] = {p0.x, p0.y, p0.z}, dd[3] = {d.x, d.y, d.z}, hh[3] = {he.x, he.y, he.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (dd[i] != 0.0f) {
+            float inv = 1.0f / dd[i];
+#pragma unroll
+            for (int sgn = 0; sgn < 2; sgn++) {
+                float t = ((sgn ? hh[i] : -hh[i]) - pp[i]) * inv;
+                if (t > lo && t < hi) {
+                    float gt = g(t);
+                    if (gt < 0.0f) { lo = t; glo = gt; } else { hi = t; ghi = gt; }
+                }
+            }
+        }
+    }
+    float t = (ghi > glo) ? lo + (hi - lo) * (-glo / (ghi - glo)) : lo;
+    return d2(t);
+}
+URGYM_HD float point_seg_dist2(float3 p, float3 a, float3 b) {
+    float3 ab = b - a, ap = p - a;
+    float den = dot(ab, ab);
+    float t = den > 0.0f ? clampf(dot(ap, ab) / den, 0.0f, 1.0f) : 0.0f;
+    float3 e = ap - t * ab;
+    return dot(e, e);
+}
+
+// World-space collision view of the robot.  Links are PyBullet link indices 1..6 (slot l-1).
+template <int GEOM> struct RobotGeom;
+
+template <> struct RobotGeom<GEOM_CAPSULE> {
+    float3 a[6], b[6];
+    const float4 *hv;     // unused
+    URGYM_HD void set_link(const ModelConst &M, int l, const Pose &T) {
+        a[l - 1] = T.p + rot(T.R, f3(M.cap_p0[l][0], M.cap_p0[l][1], M.cap_p0[l][2]));
+        b[l - 1] = T.p + rot(T.R, f3(M.cap_p1[l][0], M.cap_p1[l][1], M.cap_p1[l][2]));
+    }
+    URGYM_HD void set_neutral(const ModelConst &M) {
+#pragma unroll
+        for (int l = 1; l < 7; l++) {
+            a[l - 1] = f3(M.neutral_ca[l][0], M.neutral_ca[l][1], M.neutral_ca[l][2]);
+            b[l - 1] = f3(M.neutral_cb[l][0], M.neutral_cb[l][1], M.neutral_cb[l][2]);
+        }
+    }
+    // getClosestPoints(UR5, obstacle, linkIndexA=l)[0][8]                              pyb_setup.py:439-456
+    URGYM_HD float obstacle_dist(const ModelConst &M, int l, const ObstW &O) const {
+        float3 oa = O.c - M.obst_cap_h * O.u, ob = O.c + M.obst_cap_h * O.u;
+        return sqrtf(segseg_dist2(a[l - 1], b[l - 1], oa, ob)) - M.cap_m[l] - M.obst_cap_m;
+    }
+    URGYM_HD bool box_hit(const ModelConst &M, int l, const float *c, const float *he, float margin) const {
+        float reach = URGYM_COLLISION_MARGIN + M.cap_m[l] + margin;
+        float3 bc = f3(c[0], c[1], c[2]), bh = f3(he[0], he[1], he[2]);
+        if (seg_box_lower2(a[l - 1], b[l - 1], bc, bh) > reach * reach) return false;      // broad phase (exact bound)
+        return sqrtf(seg_box_dist2(a[l - 1], b[l - 1], bc, bh)) - M.cap_m[l] - margin <= URGYM_COLLISION_MARGIN;
+    }
+    URGYM_HD bool self_hit(const ModelConst &M, int l1, int l2) const {
+        return sqrtf(segseg_dist2(a[l1 - 1], b[l1 - 1], a[l2 - 1], b[l2 - 1])) - M.cap_m[l1] - M.cap_m[l2] <=
+               URGYM_COLLISION_MARGIN;
+    }
+};
+
+// the reference's geometry: convex hulls of the collision meshes, cylinder obstacle, GJK with Bullet's margins.
+// The bounding capsules serve as an exact-safe broad phase for the collision booleans (capsule distance is a lower
+// bound of the hull distance), the hull GJK runs only where the capsule bound cannot decide.
+template <> struct RobotGeom<GEOM_HULL> {
+    Pose T[6];
+    RobotGeom<GEOM_CAPSULE> cap;
+    const float4 *hv;     // packed hull vertices (shared memory on the device)
+    URGYM_HD void set_link(const ModelConst &M, int l, const Pose &P) { T[l - 1] = P; cap.set_link(M, l, P); }
+    URGYM_HD void set_neutral(const ModelConst &M) {
+        cap.set_neutral(M);
+#pragma unroll
+        for (int l = 1; l < 7; l++) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) T[l - 1].R[k] = M.neutral_R[l][k];
+            T[l - 1].p = f3(M.neutral_p[l][0], M.neutral_p[l][1], M.neutral_p[l][2]);
+        }
+    }
+    URGYM_HD HullW hull(const ModelConst &M, int l) const {
+        HullW H; H.v = hv + M.hull_off[l]; H.n = M.hull_off[l + 1] - M.hull_off[l]; H.T = &T[l - 1];
+        return H;
+    }
+    URGYM_HD float obstacle_dist(const ModelConst &M, int l, const ObstW &O) const {
+        // GJK converges only sublinearly against the curved wall of a cylinder (hundreds of iterations for 1e-6).
+        // Against the cylinder's AXIS SEGMENT the problem is polytope-polytope and terminates in a few iterations;
+        // when the closest vector comes out perpendicular to the axis, the nearest cylinder point lies on the side
+        // wall and distance(hull, cylinder) = distance(hull, axis segment) - radius exactly.
+        bool deep;
+        float3 v;
+        SegW S; S.a = O.c - M.obst_h * O.u; S.b = O.c + M.obst_h * O.u;
+        float ds = gjk_distance(hull(M, l), S, deep, &v);
+        if (!deep && ds > M.obst_r && fabsf(dot(v, O.u)) <= 1e-5f * ds)
+            return ds - M.obst_r - M.hull_margin - M.obst_margin;
+        CylW C; C.c = O.c; C.u = O.u; C.r = M.obst_r; C.h = M.obst_h;      // end caps / rims / penetration
+        float d = gjk_distance(hull(M, l), C, deep);
+        return d - M.hull_margin - M.obst_margin;
+    }
+    URGYM_HD bool box_hit(const ModelConst &M, int l, const float *c, const float *he, float margin) const {
+        if (!cap.box_hit(M, l, c, he, margin)) return false;
+        BoxA B; B.c = f3(c[0], c[1], c[2]); B.he = f3(he[0], he[1], he[2]);
+        bool deep;
+        float d = gjk_distance(hull(M, l), B, deep);
+        return d - M.hull_margin - margin <= URGYM_COLLISION_MARGIN;
+    }
+    URGYM_HD bool self_hit(const ModelConst &M, int l1, int l2) const {
+        if (!cap.self_hit(M, l1, l2)) return false;
+        bool deep;
+        float d = gjk_distance(hull(M, l1), hull(M, l2), deep);
+        return d - 2.0f * M.hull_margin <= URGYM_COLLISION_MARGIN;
+    }
+};
+
+// getClosestPoints(target, obstacle, distance=5)[0][8]                                  pyb_setup.py:431-437
+template <int TASK, int GEOM>
+URGYM_HD float target_obstacle_dist(const ModelConst &M, const float *goal, const ObstW &O) {
+    float3 g = f3(goal[0], goal[1], goal[2]);
+    if (GEOM == GEOM_CAPSULE) {
+        float3 oa = O.c - M.obst_cap_h * O.u, ob = O.c + M.obst_cap_h * O.u;
+        return sqrtf(point_seg_dist2(g, oa, ob)) - M.tgt_cap_m[TASK] - M.obst_cap_m;
+    }
+    CylW C; C.c = O.c; C.u = O.u; C.r = M.obst_r; C.h = M.obst_h;
+    if (TASK == TASK_OBS) return point_cyl_dist(g, C) - M.tgt_sphere_margin - M.obst_margin;   // sphere r 0.02  reach.py:270-277
+    BoxO B; B.c = g; B.he = M.tgt_box_he;                                                      // box he 0.025  reach.py:418-426
+    mat_from_quat(quat_from_euler(goal[3], goal[4], goal[5]), B.R);
+    bool deep;
+    float d = gjk_distance(B, C, deep);
+    return d - M.tgt_box_margin - M.obst_margin;
+}
+
+// PyBullet.check_collision  pyb_setup.py:382-429 (same pairs; the early-out order does not change the boolean).
+// dist[5] receives the link 2..6 <-> obstacle distances (the values get_link_distances would return).
+template <int TASK, int GEOM>
+URGYM_HD bool check_collision(const ModelConst &M, const RobotGeom<GEOM> &Rg, const ObstW &O, float *dist) {
+    bool hit = false;
+    if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
+#pragma unroll
+        for (int l = 2; l < 7; l++) {
+            dist[l - 2] = Rg.obstacle_dist(M, l, O);
+            hit = hit || (dist[l - 2] <= URGYM_COLLISION_MARGIN);
+        }
+    }
+#pragma unroll
+    for (int l = 2; l < 7; l++) {
+        hit = hit || Rg.box_hit(M, l, M.table_c, M.table_he, M.table_margin);
+        hit = hit || Rg.box_hit(M, l, M.track_c, M.track_he, M.track_margin);
+    }
+    hit = hit || Rg.self_hit(M, 1, 3) || Rg.self_hit(M, 1, 4) || Rg.self_hit(M, 1, 5) || Rg.self_hit(M, 1, 6);
+    hit = hit || Rg.self_hit(M, 2, 4) || Rg.self_hit(M, 2, 5) || Rg.self_hit(M, 2, 6);
+    hit = hit || Rg.self_hit(M, 3, 5) || Rg.self_hit(M, 3, 6);
+    return hit;
+}
+
+// ------------------------------------------------------------------------------------------------ observation
+// forward kinematics + collision view.  ee[6] = EE position + PyBullet Euler triple (UR5.py:320-325,334-340)
+template <int GEOM>
+URGYM_HD void robot_view(const ModelConst &M, const float *q, float *ee, RobotGeom<GEOM> &Rg) {
+    Pose T;
+    pose_identity(T);
+#pragma unroll
+    for (int l = 1; l < 7; l++) {
+        fk_advance(M, T, l - 1, q[l - 1]);
+        Rg.set_link(M, l, T);
+    }
+    float3 e = euler_from_mat(T.R);
+    ee[0] = T.p.x; ee[1] = T.p.y; ee[2] = T.p.z; ee[3] = e.x; ee[4] = e.y; ee[5] = e.z;
+}
+
+// task part of the observation   reach.py:189-190 (Ori), 307-308 (Obs), 454-458 (Sta), 653-657 (Dyn)
+// row[0..11] = robot obs (ee pos, ee euler, q).  vel == nullptr keeps the velocity columns as they are (stale, quirk Q4).
+template <int TASK>
+URGYM_HD void write_obs_row(float *row, const float *ee, const float *q, const float *E, const ObstW &O,
+                            const float *vel, const float *ld) {
+    typedef Traits<TASK> TT;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { row[k] = ee[k]; row[6 + k] = q[k]; }
+#pragma unroll
+    for (int k = 0; k < TT::GOAL; k++) row[12 + k] = E[k];
+    if (TASK == TASK_OBS) {             // obstacle as sampled (quirk Q3)
+#pragma unroll
+        for (int k = 0; k < 6; k++) row[15 + k] = E[3 + k];
+#pragma unroll
+        for (int k = 0; k < 5; k++) row[21 + k] = ld[k];
+    } else if (TASK == TASK_STA || TASK == TASK_DYN) {   // obstacle pose read back: position + getEulerFromQuaternion
+        float3 e = euler_from_quat(O.q);
+        row[18] = O.c.x; row[19] = O.c.y; row[20] = O.c.z; row[21] = e.x; row[22] = e.y; row[23] = e.z;
+        if (TASK == TASK_DYN) {
+            if (vel) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) row[24 + k] = vel[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++) row[30 + k] = ld[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 5; k++) row[24 + k] = ld[k];
+        }
+    }
+}
+
+// success test + the two goal distances   reach.py:212-215,348-350,543-546,755-758; utils.py:5-69
+template <int TASK>
+URGYM_HD bool goal_metrics(const float *ee, const float *E, float &d, float &ang) {
+    float dx = ee[0] - E[0], dy = ee[1] - E[1], dz = ee[2] - E[2];
+    d = sqrtf(dx * dx + dy * dy + dz * dz);
+    bool ok = d < 0.05f;
+    ang = 0.0f;
+    if (Traits<TASK>::ORI) {
+        ang = angular_distance(quat_ZYX(ee[3], ee[4], ee[5]), quat_ZYX(E[3], E[4], E[5]));
+        ok = ok && (ang < 0.0873f);
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------ step
+// RobotTaskEnv.step (core.py:303-317) + TimeLimit, without the auto-reset.  `row` receives the observation
+// (OBS floats).  vel_out (Dyn, 6 floats): ReachDyn.velocity after this step.
+template <int TASK, int GEOM>
+URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const float4 *hv, float *row, StepOut &o,
+                       float *vel_out) {
+    typedef Traits<TASK> TT;
+    // 1. UR5Ori.set_action: clip, * pi, * 0.1 (float32 like the numpy expression), teleport      UR5.py:273-279,314-317
+#pragma unroll
+    for (int j = 0; j < 6; j++) s.q[j] += (clampf(act[j], -1.0f, 1.0f) * URGYM_PI_F) * 0.1f;
+    // 2. task.set_velocity + sim.step: obstacle pose after this step                           core.py:305-309
+    ObstW O;
+    float vel[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (TT::DYN) {
+        Quat qs; float3 axis; float angle; float tw[6];
+        dyn_twist(&s.E[6], &s.E[12], tw, qs, axis, angle);
+        int moved = s.elapsed + 1 < 25 ? s.elapsed + 1 : 25;
+        O = obstacle_dyn(&s.E[6], tw, qs, axis, angle, moved);
+        if (s.elapsed < 25) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) vel[k] = tw[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) vel_out[k] = vel[k];
+    } else if (TT::HAS_OBST) {
+        O = obstacle_static(&s.E[TT::OBST]);
+    } else {
+        O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
+    }
+    // 3. FK and collision                                                                      core.py:310
+    RobotGeom<GEOM> Rg;
+    Rg.hv = hv;
+    float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    robot_view<GEOM>(M, s.q, ee, Rg);
+    bool coll = check_collision<TASK, GEOM>(M, Rg, O, dist);
+    // 4. observation: carries link_dist from BEFORE this step's reward (quirk Q1)               core.py:311
+    write_obs_row<TASK>(row, ee, s.q, s.E, O, vel, s.ld);
+    // 5. termination                                                                           core.py:313-315
+    float d, ang;
+    bool succ = goal_metrics<TASK>(ee, s.E, d, ang);
+    o.collision = coll;
+    o.terminated = succ || coll;
+    o.success = o.terminated && !coll;
+    // 6. reward                                                                                core.py:316
+    float r;
+    if (TASK == TASK_ORI) {             // reach.py:221-236
+        r = (succ ? 200.0f : 0.0f) - 70.0f * d - 30.0f * ang - (coll ? 500.0f : 0.0f);
+    } else if (TASK == TASK_OBS) {      // reach.py:356-374
+        r = (succ ? 200.0f : 0.0f) - (coll ? 500.0f : 0.0f) - 100.0f * d;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            if (dist[k] < 0.2f) acc += 100.0f * (dist[k] - s.ld[k]);
+            s.ld[k] = dist[k];
+        }
+        r += acc;
+    } else {                            // reach.py:552-573, 764-785
+        if (coll) r = -500.0f;
+        else if (succ) r = 200.0f;
+        else {
+            const float w[5] = {8.0f / 13.0f * 50.0f, 2.4f / 13.0f * 50.0f, 1.2f / 13.0f * 50.0f, 1.2f / 13.0f * 50.0f,
+                                0.2f / 13.0f * 50.0f};
+            r = -70.0f * d - 30.0f * ang;
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                if (dist[k] < 0.2f) acc += w[k] * (dist[k] - s.ld[k]);
+                s.ld[k] = dist[k];
+            }
+            r += acc;
+        }
+    }
+    o.reward = r;
+    // 7. TimeLimit
+    s.elapsed += 1;
+    o.truncated = s.elapsed >= URGYM_MAX_STEPS;
+    s.ep_ret += r;
+}
+
+// RobotTaskEnv._get_obs (core.py:252-261) from the current state, no stepping.  stale_vel: ReachDyn.velocity as
+// stored at the last reset, shown while elapsed == 0 (quirk Q4).
+template <int TASK, int GEOM>
+URGYM_HD void env_observe(const ModelConst &M, const EnvState &s, const float *stale_vel, float *row) {
+    typedef Traits<TASK> TT;
+    ObstW O;
+    float vel[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (TT::DYN) {
+        Quat qs; float3 axis; float angle; float tw[6];
+        dyn_twist(&s.E[6], &s.E[12], tw, qs, axis, angle);
+        O = obstacle_dyn(&s.E[6], tw, qs, axis, angle, s.elapsed < 25 ? s.elapsed : 25);
+#pragma unroll
+        for (int k = 0; k < 6; k++) vel[k] = s.elapsed == 0 ? stale_vel[k] : (s.elapsed <= 25 ? tw[k] : 0.0f);
+    } else if (TT::HAS_OBST) {
+        O = obstacle_static(&s.E[TT::OBST]);
+    } else {
+        O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
+    }
+    RobotGeom<GEOM_CAPSULE> Rg;     // only the EE pose is needed
+    Rg.hv = nullptr;
+    float ee[6];
+    robot_view<GEOM_CAPSULE>(M, s.q, ee, Rg);
+    write_obs_row<TASK>(row, ee, s.q, s.E, O, vel, s.ld);
+}
+
+// tail of set_goal_and_obstacle / reset: collision flag and link_dist = last_dist at the current state
+// reach.py:322-324,333-335,477-479,501-503,679-681,711-713
+template <int TASK, int GEOM>
+URGYM_HD bool env_refresh(const ModelConst &M, EnvState &s, const float4 *hv) {
+    typedef Traits<TASK> TT;
+    ObstW O;
+    if (TT::DYN) {
+        Quat qs; float3 axis; float angle; float tw[6];
+        dyn_twist(&s.E[6], &s.E[12], tw, qs, axis, angle);
+        O = obstacle_dyn(&s.E[6], tw, qs, axis, angle, s.elapsed < 25 ? s.elapsed : 25);
+    } else if (TT::HAS_OBST) {
+        O = obstacle_static(&s.E[TT::OBST]);
+    } else {
+        O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
+    }
+    RobotGeom<GEOM> Rg;
+    Rg.hv = hv;
+    float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    robot_view<GEOM>(M, s.q, ee, Rg);
+    bool coll = check_collision<TASK, GEOM>(M, Rg, O, dist);
+    if (TT::HAS_OBST) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) s.ld[k] = dist[k];
+    }
+    return coll;
+}
+
+// ------------------------------------------------------------------------------------------------ reset
+// uniform draw `slot` of rejection iteration rs.iter: Philox block slot/4, lane slot%4
+struct Draws {
+    uint4 b[5];
+    URGYM_HD float u(int slot) const {
+        uint4 x = b[slot >> 2];
+        int k = slot & 3;
+        return u01(k == 0 ? x.x : (k == 1 ? x.y : (k == 2 ? x.z : x.w)));
+    }
+};
+URGYM_HD float lerp_u(float lo, float hi, float u) { return lo + (hi - lo) * u; }     // np_random.uniform(low, high)
+
+// Reach*.reset (reach.py:197-200,313-326,465-481,664-683) with _sample_goal / _sample_obstacle
+// (reach.py:206-210,337-346,505-516,715-726): fills E, returns the number of rejection iterations used.
+template <int TASK, int GEOM>
+URGYM_HD int sample_episode(const ModelConst &M, ResetStream rs, float *E) {
+    typedef Traits<TASK> TT;
+    float3 glo, ghi, olo, ohi;
+    goal_range<TASK>(glo, ghi);
+    obstacle_range<TASK>(olo, ohi);
+    int k = 0;
+    for (;;) {
+        rs.iter = (uint32_t)k;
+        Draws D;
+        bool fail = false;
+        if (TASK == TASK_ORI) {                     // slots: goal 0-2, goal_roll 3, goal_yaw 4
+            D.b[0] = rs.block(0); D.b[1] = rs.block(1);
+            E[0] = lerp_u(glo.x, ghi.x, D.u(0)); E[1] = lerp_u(glo.y, ghi.y, D.u(1)); E[2] = lerp_u(glo.z, ghi.z, D.u(2));
+            E[4] = 0.0f;
+            euler_constrained(D.u(3), D.u(4), E[3], E[5]);
+        } else if (TASK == TASK_OBS) {              // goal 0-2, obstacle 3-5, sign 6, roll 7, pitch 8
+            D.b[0] = rs.block(0); D.b[1] = rs.block(1); D.b[2] = rs.block(2);
+            E[0] = lerp_u(glo.x, ghi.x, D.u(0)); E[1] = lerp_u(glo.y, ghi.y, D.u(1)); E[2] = lerp_u(glo.z, ghi.z, D.u(2));
+            E[3] = lerp_u(olo.x, ohi.x, D.u(3)); E[4] = lerp_u(olo.y, ohi.y, D.u(4)); E[5] = lerp_u(olo.z, ohi.z, D.u(5));
+            euler_obstacle(D.u(6), D.u(7), D.u(8), E[6], E[7]);
+            E[8] = 0.0f;
+            fail = target_obstacle_dist<TASK, GEOM>(M, E, obstacle_static(&E[3])) < 0.1f;        // reach.py:321
+        } else if (TASK == TASK_STA) {              // goal 0-2, roll 3, yaw 4, obstacle 5-7, sign 8, roll 9, pitch 10
+            D.b[0] = rs.block(0); D.b[1] = rs.block(1); D.b[2] = rs.block(2);
+            E[0] = lerp_u(glo.x, ghi.x, D.u(0)); E[1] = lerp_u(glo.y, ghi.y, D.u(1)); E[2] = lerp_u(glo.z, ghi.z, D.u(2));
+            E[4] = 0.0f;
+            euler_constrained(D.u(3), D.u(4), E[3], E[5]);
+            E[6] = lerp_u(olo.x, ohi.x, D.u(5)); E[7] = lerp_u(olo.y, ohi.y, D.u(6)); E[8] = lerp_u(olo.z, ohi.z, D.u(7));
+            euler_obstacle(D.u(8), D.u(9), D.u(10), E[9], E[10]);
+            E[11] = 0.0f;
+            fail = target_obstacle_dist<TASK, GEOM>(M, E, obstacle_static(&E[6])) < 0.1f;        // reach.py:473
+        } else {                                    // Dyn: start 0-2, end 3-5, goal 6-8, roll 9, yaw 10, start s/r/p 11-13, end 14-16
+            D.b[0] = rs.block(0); D.b[1] = rs.block(1);
+            E[6] = lerp_u(olo.x, ohi.x, D.u(0)); E[7] = lerp_u(olo.y, ohi.y, D.u(1)); E[8] = lerp_u(olo.z, ohi.z, D.u(2));
+            E[12] = lerp_u(olo.x, ohi.x, D.u(3)); E[13] = lerp_u(olo.y, ohi.y, D.u(4)); E[14] = lerp_u(olo.z, ohi.z, D.u(5));
+            float dx = E[12] - E[6], dy = E[13] - E[7], dz = E[14] - E[8];
+            fail = sqrtf(dx * dx + dy * dy + dz * dz) < 1.0f;                                     // reach.py:674-675
+            if (!fail || k + 1 >= URGYM_MAX_RESET_ITERS) {      // the other draws matter only for a surviving iteration
+                D.b[2] = rs.block(2); D.b[3] = rs.block(3); D.b[4] = rs.block(4);
+                E[0] = lerp_u(glo.x, ghi.x, D.u(6)); E[1] = lerp_u(glo.y, ghi.y, D.u(7)); E[2] = lerp_u(glo.z, ghi.z, D.u(8));
+                E[4] = 0.0f;
+                euler_constrained(D.u(9), D.u(10), E[3], E[5]);
+                euler_obstacle(D.u(11), D.u(12), D.u(13), E[9], E[10]);
+                E[11] = 0.0f;
+                euler_obstacle(D.u(14), D.u(15), D.u(16), E[15], E[16]);
+                E[17] = 0.0f;
+                fail = fail || (target_obstacle_dist<TASK, GEOM>(M, E, obstacle_static(&E[12])) < 0.1f);
+            }
+        }
+        k++;
+        if (!fail || k >= URGYM_MAX_RESET_ITERS) break;
+    }
+    return k;
+}
+
+// RobotTaskEnv.reset (core.py:263-273): neutral pose, new episode constants, link_dist = last_dist at the reset
+// pose, first observation.  The velocity columns of `row` are left untouched (quirk Q4: the caller puts the
+// previous ReachDyn.velocity there).  Returns the rejection iterations used.
+template <int TASK, int GEOM>
+URGYM_HD int env_reset(const ModelConst &M, EnvState &s, ResetStream rs, const float4 *hv, float *row) {
+    typedef Traits<TASK> TT;
+    int iters = sample_episode<TASK, GEOM>(M, rs, s.E);
+#pragma unroll
+    for (int j = 0; j < 6; j++) s.q[j] = M.neutral_q[j];
+    s.elapsed = 0;
+    s.ep_ret = 0.0f;
+    ObstW O;
+    if (TT::HAS_OBST) {
+        O = obstacle_static(&s.E[TT::OBST]);           // Dyn: obstacle placed at START after sampling   reach.py:678
+        RobotGeom<GEOM> Rg;
+        Rg.hv = hv;
+        Rg.set_neutral(M);
+#pragma unroll
+        for (int l = 2; l < 7; l++) s.ld[l - 2] = Rg.obstacle_dist(M, l, O);        // reach.py:323-324,478-479,680-681
+    } else {
+        O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
+#pragma unroll
+        for (int k = 0; k < 5; k++) s.ld[k] = 0.0f;
+    }
+    write_obs_row<TASK>(row, M.neutral_ee, s.q, s.E, O, nullptr, s.ld);
+    return iters;
+}
+
+}  // namespace urgym

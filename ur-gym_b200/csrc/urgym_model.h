@@ -1,0 +1,96 @@
+// urgym_model.h -- host-side construction of the constants the kernels read from __constant__ memory, from the
+// generated robot description (ur5e_model_data.h) and the scene the reach tasks create (reach.py / pyb_setup.py).
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include "ur5e_model_data.h"
+#include "urgym_device.cuh"
+
+namespace urgym {
+
+// double-precision FK on the host, only to derive the constants of the (fixed) reset pose
+static void host_fk(const double q[6], double pos[7][3], double R[7][9]) {
+    for (int k = 0; k < 9; k++) R[0][k] = (k % 4 == 0) ? 1.0 : 0.0;
+    pos[0][0] = pos[0][1] = pos[0][2] = 0.0;
+    for (int j = 0; j < 6; j++) {
+        const double *X = &UR5E_JOINT_XYZ[3 * j], *F = &UR5E_JOINT_ROT[9 * j];
+        double A[9];
+        for (int r = 0; r < 3; r++) {
+            pos[j + 1][r] = pos[j][r] + R[j][3 * r] * X[0] + R[j][3 * r + 1] * X[1] + R[j][3 * r + 2] * X[2];
+            for (int c = 0; c < 3; c++) A[3 * r + c] = R[j][3 * r] * F[c] + R[j][3 * r + 1] * F[3 + c] + R[j][3 * r + 2] * F[6 + c];
+        }
+        double c = cos(q[j]), s = sin(q[j]);
+        for (int r = 0; r < 3; r++) {
+            R[j + 1][3 * r] = A[3 * r] * c + A[3 * r + 1] * s;
+            R[j + 1][3 * r + 1] = A[3 * r + 1] * c - A[3 * r] * s;
+            R[j + 1][3 * r + 2] = A[3 * r + 2];
+        }
+    }
+}
+
+static void build_model_const(ModelConst &M) {
+    memset(&M, 0, sizeof(M));
+    for (int j = 0; j < 6; j++) {
+        for (int k = 0; k < 3; k++) M.joint_xyz[j][k] = (float)UR5E_JOINT_XYZ[3 * j + k];
+        for (int k = 0; k < 9; k++) M.joint_rot[j][k] = (float)UR5E_JOINT_ROT[9 * j + k];
+    }
+    const double hull_margin = 0.001;                       // URDF mesh links, Bullet default collision margin
+    for (int l = 0; l < 7; l++) {
+        for (int k = 0; k < 3; k++) {
+            M.cap_p0[l][k] = (float)UR5E_CAPSULE_P0[3 * l + k];
+            M.cap_p1[l][k] = (float)UR5E_CAPSULE_P1[3 * l + k];
+        }
+        M.cap_m[l] = (float)(UR5E_CAPSULE_R[l] + hull_margin);
+    }
+    for (int l = 0; l < 8; l++) M.hull_off[l] = UR5E_HULL_OFFSET[l];
+    M.hull_margin = (float)hull_margin;
+    const double pm = 0.001;                                // createCollisionShape primitives: margin 0.001, core shrunk
+    // create_table(1.1, 1.8, 0.92, x_offset=0.5, z_offset=-0.12)   reach.py:169; pyb_setup.py:802-811
+    const double tc[3] = {0.5, 0.0, -0.12 - 0.46}, th[3] = {0.55, 0.9, 0.46};
+    // create_track(0.2, 1.1, 0.12, x_offset=0, z_offset=0)         reach.py:170; pyb_setup.py:835-844
+    const double kc[3] = {0.0, 0.0, -0.06}, kh[3] = {0.1, 0.55, 0.06};
+    for (int k = 0; k < 3; k++) {
+        M.table_c[k] = (float)tc[k]; M.table_he[k] = (float)(th[k] - pm);
+        M.track_c[k] = (float)kc[k]; M.track_he[k] = (float)(kh[k] - pm);
+    }
+    M.table_margin = M.track_margin = (float)pm;
+    // obstacle cylinder radius 0.05, height 0.4                    reach.py:279-283,427-431,626-630
+    M.obst_r = (float)(0.05 - pm); M.obst_h = (float)(0.2 - pm); M.obst_margin = (float)pm;
+    M.tgt_box_he = (float)(0.025 - pm); M.tgt_box_margin = (float)pm;   // reach.py:418-426
+    M.tgt_sphere_margin = 0.02f;                                         // reach.py:270-277
+    // capsule mode: smallest bounding capsule of the cylinder (segment half length = half height, radius = radius);
+    // target: the Obs sphere itself, the bounding sphere of the Sta/Dyn cube
+    M.obst_cap_h = 0.2f; M.obst_cap_m = 0.05f;
+    M.tgt_cap_m[0] = 0.0f; M.tgt_cap_m[1] = 0.02f;
+    M.tgt_cap_m[2] = M.tgt_cap_m[3] = (float)(0.025 * 1.7320508075688772);
+    // reset pose                                                   UR5.py:262
+    const double qn[6] = {0.0, -1.5708, 0.0, -1.5708, 0.0, 0.0};
+    double pos[7][3], R[7][9];
+    host_fk(qn, pos, R);
+    for (int j = 0; j < 6; j++) M.neutral_q[j] = (float)qn[j];
+    for (int l = 0; l < 7; l++) {
+        for (int r = 0; r < 3; r++) {
+            double a = pos[l][r], b = pos[l][r];
+            for (int c = 0; c < 3; c++) {
+                a += R[l][3 * r + c] * UR5E_CAPSULE_P0[3 * l + c];
+                b += R[l][3 * r + c] * UR5E_CAPSULE_P1[3 * l + c];
+            }
+            M.neutral_ca[l][r] = (float)a; M.neutral_cb[l][r] = (float)b;
+            M.neutral_p[l][r] = (float)pos[l][r];
+        }
+        for (int k = 0; k < 9; k++) M.neutral_R[l][k] = (float)R[l][k];
+    }
+    // EE pose = link 6 frame (ee_link: identity fixed joint, no inertial)   UR5.py:263,334-340
+    {
+        const double *E = R[6];
+        double sarg = -E[6], roll, pitch, yaw;
+        // |sarg| is far from the gimbal branch at the reset pose; regular getEulerFromQuaternion formulas
+        pitch = asin(sarg); roll = atan2(E[7], E[8]); yaw = atan2(E[3], E[0]);
+        M.neutral_ee[0] = (float)pos[6][0]; M.neutral_ee[1] = (float)pos[6][1]; M.neutral_ee[2] = (float)pos[6][2];
+        M.neutral_ee[3] = (float)roll; M.neutral_ee[4] = (float)pitch; M.neutral_ee[5] = (float)yaw;
+    }
+}
+
+
+}  // namespace urgym
