@@ -1,0 +1,286 @@
+#!/usr/bin/env python3
+"""bench.py -- env-steps/s of the batched UR5e reach simulator on N B200s, with roofline, end-to-end and CPU-baseline
+figures on one JSON line (the contract is in the task statement; DESIGN.md section "Measurement" explains each key).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--task ID] [--envs-per-gpu M]
+                    [--geometry capsule|hull]
+
+Workload (BASELINE.json metric): UR5DynReach-v1, 1 Mi envs per GPU (config[4]: 8 Mi envs on 8 GPUs), i.i.d. U(-1,1)
+actions resident in HBM, auto-reset on.  One step = one launch of the fused step kernel over all envs of the rank."""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+OBS_DIM = {"UR5OriReach-v1": 18, "UR5ObsReach-v1": 26, "UR5StaReach-v1": 29, "UR5DynReach-v1": 35}
+# algorithmic bytes per env-step and per reset (SURVEY.md section 8d / BASELINE.md section 5)
+BYTES_STEP = {"UR5OriReach-v1": 215, "UR5ObsReach-v1": 287, "UR5StaReach-v1": 323, "UR5DynReach-v1": 371}
+BYTES_RESET = {"UR5OriReach-v1": 100, "UR5ObsReach-v1": 144, "UR5StaReach-v1": 168, "UR5DynReach-v1": 240}
+METRIC = "env-steps/sec"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--task", default="UR5DynReach-v1", choices=sorted(OBS_DIM))
+    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--geometry", default="capsule", choices=["capsule", "hull"])
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall-clock budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": f"{args.task}, {args.envs_per_gpu} envs per GPU, random actions U(-1,1) resident in HBM, "
+                        f"auto-reset on, {args.geometry} geometry",
+            "task": args.task, "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
+            "geometry": args.geometry, "sharding": f"env index ranges over {world} rank(s), no data-path collective",
+            "l2": "per-step traffic (state + actions + outputs) exceeds the 126 MB L2; an 8-deep ring of action buffers"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def _cpu_worker(task, geom, seed, n_steps, conn):
+    import numpy as np
+    from oracle import oracle_env as oe
+    env = oe.make(task, geom=geom, stream=oe.PhiloxStream(seed), env_index=seed, first_event=1)
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(-1, 1, (max(n_steps, 1), 6)).astype(np.float32)
+    conn.send("ready")
+    conn.recv()
+    t0 = time.perf_counter()
+    ev = 1
+    for k in range(n_steps):                     # demo.py:10-15 without the GUI
+        o, r, term, trunc, info = env.step(acts[k])
+        ev += 1
+        if term or trunc:
+            env.reset(event=ev)
+    conn.send(time.perf_counter() - t0)
+
+
+def cpu_env_steps_per_s(task, geometry, steps_per_proc, procs):
+    """P processes, one oracle env each (the reference allows one env per process: SURVEY.md Q10), random actions,
+    reset on done.  Returns (env-steps/s over all processes, seconds)."""
+    import multiprocessing as mp
+    from oracle import oracle_env as oe
+    oe.build_oracle()
+    geom = oe.GEOM_CAPSULE if geometry == "capsule" else oe.GEOM_HULL
+    ctx = mp.get_context("fork")
+    pipes, ps = [], []
+    for i in range(procs):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=_cpu_worker, args=(task, geom, i, steps_per_proc, b), daemon=True)
+        p.start(); pipes.append(a); ps.append(p)
+    for a in pipes:
+        a.recv()
+    t0 = time.perf_counter()
+    for a in pipes:
+        a.send("go")
+    for a in pipes:
+        a.recv()
+    dt = time.perf_counter() - t0
+    for p in ps:
+        p.join()
+    return procs * steps_per_proc / dt, dt
+
+
+def calibrate_cpu(task, geometry, seconds, procs):
+    rate1, _ = cpu_env_steps_per_s(task, geometry, 150, procs)
+    per_proc = max(200, int(rate1 / procs * seconds))
+    rate, dt = cpu_env_steps_per_s(task, geometry, per_proc, procs)
+    return rate, per_proc, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    sample = 250                                  # env steps per process per bench "step"
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_env_steps_per_s(args.task, args.geometry, 50, procs)
+    rate, dt = cpu_env_steps_per_s(args.task, args.geometry, sample * max(args.steps, 1), procs)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
+                             "sample": f"{procs} processes x {sample * max(args.steps, 1)} env steps of {args.task} (one oracle env per "
+                                       "process, reset on done); the reference itself needs PyBullet, which is not installable "
+                                       "here, so this is the CPU restatement (oracle/), not PyBullet"},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        import statistics
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import urgym_b200 as ug
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the simulator has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    n = args.envs_per_gpu
+    env = ug.UR5VecEnv(args.task, n, device=local_rank, seed=0, env_index_offset=rank * n, geometry=args.geometry,
+                       goal_buffers=True)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ring = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(8)]
+    env.reset()
+    warm = max(args.warmup, 3)
+    for k in range(warm):
+        env.step(ring[k % 8])
+    env.stats(reset=True)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = env.launch_count
+    barrier()
+    sampler.start()
+    e0.record()
+    for k in range(args.steps):
+        env.step(ring[k % 8])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = env.launch_count - launches0
+    barrier()
+    st = env.stats(reset=True)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        st = ug.allreduce_stats(st, device=dev)
+    ms_max = float(t.item())
+    value = n * world * args.steps / (ms_max * 1e-3)
+
+    # roofline of the step kernel on this rank: algorithmic bytes per launch / average launch duration
+    n_done_rank = env_done = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    episodes_per_launch = st["episodes"] / world / max(args.steps, 1)
+    bytes_per_launch = n * BYTES_STEP[args.task] + episodes_per_launch * BYTES_RESET[args.task]
+    achieved = bytes_per_launch / (ms * 1e-3 / max(args.steps, 1)) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_step_kernel_summary.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
+                "kernel": f"urgym_step_kernel<{args.task}, {args.geometry}>",
+                "bytes_per_env_step": BYTES_STEP[args.task], "bytes_per_reset": BYTES_RESET[args.task],
+                "resets_per_launch": episodes_per_launch}
+
+    # end to end through the host-buffer entry point: pinned host actions in, observations / rewards / flags out
+    buf = env.alloc_host_buffers(terminal_obs=False)
+    host_ring = [r.cpu().pin_memory() for r in ring[:2]]
+    for k in range(2):
+        env.step_host(host_ring[k % 2], buf)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.e2e_steps):
+        env.step_host(host_ring[k % 2], buf)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    D = OBS_DIM[args.task]
+    e2e = {"value": n * world * args.e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 24,
+           "d2h_bytes_per_step": n * (4 * D + 4 + 3), "steps": args.e2e_steps,
+           "path": "urgym_step_host: pinned host actions -> device, step kernel, observation + reward + 3 flag arrays -> pinned host"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
+            "e2e": e2e, "gpu_launches": launches, "clocks": sampler.result(),
+            "episode_stats": ug.summarize(st)}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            procs = os.cpu_count() or 1
+            rate, per_proc, cdt = calibrate_cpu(args.task, args.geometry, args.cpu_seconds, procs)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
+                                    "sample": f"{procs} processes x {per_proc} env steps of {args.task} on the oracle port "
+                                              f"({cdt:.1f} s wall); PyBullet itself is not installable here"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

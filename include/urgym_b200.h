@@ -135,6 +135,8 @@ int urgym_reset_host(urgym_env_t *h, const uint8_t *mask, float *obs, float *ach
 int urgym_set_autoreset(urgym_env_t *h, int enabled);
 /* the reset-event counter (position of the reset stream); together with the URGYM_F_* fields it checkpoints a handle */
 int urgym_get_event(const urgym_env_t *h, uint32_t *event);
+/* re-key the reset stream: RobotTaskEnv.reset(seed=...) re-creates task.np_random (core.py:267) */
+int urgym_set_seed(urgym_env_t *h, uint64_t seed);
 int urgym_set_event(urgym_env_t *h, uint32_t event);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */

@@ -27,7 +27,7 @@ def _rotation_angle(e1, e2):
     return (R.from_euler("xyz", e1).inv() * R.from_euler("xyz", e2)).magnitude()
 
 
-GIMBAL_ZONE = np.deg2rad(3.0)
+GIMBAL_ZONE = np.deg2rad(10.0)
 gimbal_fallbacks = [0]
 
 
@@ -37,7 +37,7 @@ LD_COLS = {"UR5OriReach-v1": [], "UR5ObsReach-v1": list(range(21, 26)), "UR5StaR
 
 def obs_close(env_id, got, want, ld_tol=None):
     """max position-like error and max angle-like error between two observation rows.  Euler triples are compared
-    component-wise (mod 2 pi); within 3 degrees of gimbal lock, where roll and yaw are individually ill-conditioned
+    component-wise (mod 2 pi); within 10 degrees of gimbal lock (roll and yaw error amplification 1/cos(pitch) > 5.7), where roll and yaw are individually ill-conditioned
     in any precision, the rotation they encode is compared instead."""
     cols = EULER_COLS[env_id]
     mask = np.zeros(len(want), bool); mask[cols] = True

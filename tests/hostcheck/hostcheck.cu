@@ -134,8 +134,9 @@ void hc_observe(int task, int64_t n, float *q, int32_t *elapsed, float *ep_ret, 
 void hc_ee_pose(int64_t n, const float *q, float *ee) {
     init();
     for (int64_t i = 0; i < n; i++) {
-        RobotGeom<GEOM_CAPSULE> Rg; Rg.hv = nullptr;
-        robot_view<GEOM_CAPSULE>(g_M, q + i * 6, ee + i * 6, Rg);
+        ObstW O; O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
+        float du[5];
+        robot_pass<TASK_ORI, GEOM_CAPSULE>(g_M, q + i * 6, O, nullptr, false, ee + i * 6, du[0], du[1], du[2], du[3], du[4]);
     }
 }
 void hc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {

@@ -1,0 +1,273 @@
+"""GPU tier: the CUDA library, called through its C ABI (ctypes) by the Python host layer, against the oracle.
+
+Same harness as the CPU tier (tests/_parity.py): identical actions, identical counter-based reset stream, every
+observation / reward / flag / terminal observation / post-reset observation of every step compared at the
+north-star tolerances.  Then size-independent properties at BASELINE.json's full size (1 Mi envs per GPU)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_env as oe
+from tests._parity import run_parity
+
+pytestmark = pytest.mark.gpu
+TASKS = ["UR5OriReach-v1", "UR5ObsReach-v1", "UR5StaReach-v1", "UR5DynReach-v1"]
+
+
+@pytest.fixture(scope="module")
+def ug():
+    import urgym_b200
+    return urgym_b200
+
+
+@pytest.mark.parametrize("env_id", TASKS)
+def test_capsule_rollout_parity(env_id, ug):
+    from tests._gpu import GpuSim
+    n, steps = 200, 110        # 200 = one full 128-row tile + a ragged one; 110 steps cross the TimeLimit
+    st = run_parity(GpuSim(env_id, oe.GEOM_CAPSULE, n, seed=7), env_id, oe.GEOM_CAPSULE, n, steps, seed=7)
+    assert st["steps"] > 0.9 * n * steps and st["resets"] > 0, st
+    print(env_id, st)
+
+
+@pytest.mark.parametrize("env_id", TASKS)
+def test_capsule_small_actions_reach_timelimit(env_id, ug):
+    """small actions keep the arm away from collisions so episodes run into the 100-step TimeLimit"""
+    from tests._gpu import GpuSim
+    n, steps = 64, 205
+    st = run_parity(GpuSim(env_id, oe.GEOM_CAPSULE, n, seed=11, offset=5000), env_id, oe.GEOM_CAPSULE, n, steps, seed=11,
+                    offset=5000, action_scale=0.05)
+    assert st["truncations"] > 0, st
+
+
+@pytest.mark.parametrize("env_id", TASKS)
+def test_hull_rollout_parity(env_id, ug):
+    from tests._gpu import GpuSim
+    n, steps = 40, 40
+    st = run_parity(GpuSim(env_id, oe.GEOM_HULL, n, seed=3, offset=77), env_id, oe.GEOM_HULL, n, steps, seed=3, offset=77,
+                    ld_tol=5e-5, rew_atol=1e-2)
+    assert st["steps"] > 0.85 * n * steps, st
+
+
+@pytest.mark.parametrize("env_id", TASKS)
+def test_gpu_equals_host_instantiation_bitwise_flags(env_id, ug):
+    """the kernel and tests/hostcheck run the same functions; booleans must agree except next to a threshold, floats
+    to FP32 round-off (FMA contraction differs between nvcc and g++)"""
+    from tests._gpu import GpuSim
+    from tests._hostcheck import HostCheckSim
+    n, steps = 1000, 30
+    g, h = GpuSim(env_id, 1, n, seed=5), HostCheckSim(env_id, 1, n, seed=5)
+    og, oh = g.reset(), h.reset()
+    np.testing.assert_allclose(og, oh, atol=2e-6)
+    rng = np.random.default_rng(0)
+    alive = np.ones(n, bool)
+    for t in range(steps):
+        a = rng.uniform(-1.1, 1.1, (n, 6)).astype(np.float32)
+        rg, rh = g.step(a), h.step(a)
+        same = (rg["terminated"] == rh["terminated"]) & (rg["truncated"] == rh["truncated"]) & (rg["is_success"] == rh["is_success"])
+        alive &= same
+        np.testing.assert_allclose(rg["terminal_obs"][alive], rh["terminal_obs"][alive], atol=5e-6)
+        np.testing.assert_allclose(rg["reward"][alive], rh["reward"][alive], rtol=2e-6, atol=2e-4)
+    assert alive.mean() > 0.995
+
+
+def test_sharding_invariance(ug):
+    """the same global env index produces the same episodes whatever the shard layout"""
+    env_id, n = "UR5DynReach-v1", 1024
+    whole = ug.UR5VecEnv(env_id, n, seed=42)
+    parts = [ug.UR5VecEnv(env_id, hi - lo, seed=42, env_index_offset=lo)
+             for lo, hi in (ug.shard_range(n, r, 3) for r in range(3))]
+    o = whole.reset()["observation"].clone()
+    op = torch.cat([p.reset()["observation"] for p in parts])
+    assert torch.equal(o, op)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(40):
+        a = torch.rand((n, 6), device="cuda", generator=g) * 2 - 1
+        ow, rw, tw, cw, iw = whole.step(a)
+        outs, lo = [], 0
+        for p in parts:
+            outs.append(p.step(a[lo:lo + p.num_envs].contiguous())); lo += p.num_envs
+        assert torch.equal(ow["observation"], torch.cat([x[0]["observation"] for x in outs]))
+        assert torch.equal(rw, torch.cat([x[1] for x in outs]))
+        assert torch.equal(tw, torch.cat([x[2] for x in outs]))
+        assert torch.equal(cw, torch.cat([x[3] for x in outs]))
+    sw = whole.stats()
+    sp = [p.stats() for p in parts]
+    for k in sw:
+        assert sw[k] == sum(s[k] for s in sp), k      # fixed-point return sum: exact, order-independent
+    assert sw["episodes"] > 0 and sw["env_steps"] == n * 40
+
+
+def test_fused_autoreset_equals_explicit_reset(ug):
+    """step with auto-reset == step without it followed by reset(mask = done) at the same reset event"""
+    env_id, n = "UR5StaReach-v1", 4096
+    a_env = ug.UR5VecEnv(env_id, n, seed=9)
+    b_env = ug.UR5VecEnv(env_id, n, seed=9, auto_reset=False)
+    a_env.reset(); b_env.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(25):
+        act = torch.rand((n, 6), device="cuda", generator=g) * 2.4 - 1.2
+        oa, ra, ta, ca, ia = a_env.step(act)
+        ob, rb, tb, cb, ib = b_env.step(act)
+        assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(ca, cb)
+        done = (tb | cb)
+        assert torch.equal(ia["terminal_observation"][done.bool()], ob["observation"][done.bool()])
+        ev = ctypes.c_uint32()
+        b_env.L.urgym_get_event(b_env.h, ctypes.byref(ev))
+        b_env.L.urgym_set_event(b_env.h, ev.value - 1)
+        ob2 = b_env.reset(mask=done)
+        assert torch.equal(oa["observation"], ob2["observation"])
+    for name in ("q", "goal", "obstacle", "link_dist", "elapsed", "ep_return"):
+        assert torch.equal(a_env.get_state(name), b_env.get_state(name)), name
+
+
+def test_full_size_properties(ug):
+    """BASELINE config: UR5DynReach-v1, 1 Mi envs on one GPU.  Size-independent properties."""
+    env_id, n, steps = "UR5DynReach-v1", 1 << 20, 120
+    env = ug.UR5VecEnv(env_id, n, seed=2026)
+    first = env.reset()["observation"].clone()
+    assert torch.isfinite(first).all()
+    # goals / obstacles inside the sampling boxes (reach.py:584-587), start-end at least 1 m apart (reach.py:674-675)
+    goal, start, end = env.get_state("goal"), env.get_state("obstacle"), env.get_state("obstacle_end")
+    lo, hi = torch.tensor([0.4, -0.5, 0.0], device="cuda"), torch.tensor([0.75, 0.5, 0.2], device="cuda")
+    assert ((goal[:, :3] >= lo) & (goal[:, :3] <= hi)).all()
+    olo, ohi = torch.tensor([0.5, -0.8, 0.25], device="cuda"), torch.tensor([1.2, 0.8, 0.75], device="cuda")
+    assert ((start[:, :3] >= olo) & (start[:, :3] <= ohi) & (end[:, :3] >= olo) & (end[:, :3] <= ohi)).all()
+    assert ((end[:, :3] - start[:, :3]).norm(dim=1) >= 1.0 - 1e-6).all()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ep_len = torch.zeros(n, dtype=torch.int32, device="cuda")
+    n_done = n_succ = n_trunc = 0
+    ret_sum = 0.0
+    ep_ret = torch.zeros(n, dtype=torch.float64, device="cuda")
+    small = torch.arange(n, device="cuda") % 4 == 0        # a quarter of the envs take tiny actions -> hit the TimeLimit
+    for t in range(steps):
+        a = torch.rand((n, 6), device="cuda", generator=g) * 2 - 1
+        a[small] *= 0.03
+        obs, rew, term, trunc, info = env.step(a)
+        assert torch.isfinite(obs["observation"]).all() and torch.isfinite(rew).all()
+        ep_len += 1
+        ep_ret += rew.double()
+        done = (term | trunc).bool()
+        assert not (info["is_success"].bool() & ~term.bool()).any()            # success implies terminated (core.py:313-315)
+        assert torch.equal(trunc.bool(), ep_len >= 100)                          # TimeLimit
+        assert (env.get_state("elapsed")[~done] == ep_len[~done]).all()
+        # a finished env restarts at the neutral pose with a fresh goal
+        q = obs["observation"][:, 6:12]
+        neutral = torch.tensor([0.0, -1.5708, 0.0, -1.5708, 0.0, 0.0], device="cuda")
+        assert (q[done] == neutral).all()
+        n_done += int(done.sum()); n_succ += int(info["is_success"].sum()); n_trunc += int((trunc.bool() & ~term.bool()).sum())
+        ret_sum += float(ep_ret[done].sum())
+        ep_len[done] = 0; ep_ret[done] = 0
+    st = env.stats()
+    assert st["env_steps"] == n * steps and st["episodes"] == n_done and st["successes"] == n_succ and st["truncations"] == n_trunc
+    assert n_trunc > 0
+    assert abs(st["return_sum"] - ret_sum) <= 1e-4 * abs(ret_sum) + 1.0
+    # determinism: the same seed and actions reproduce the run bit for bit
+    env2 = ug.UR5VecEnv(env_id, n, seed=2026)
+    assert torch.equal(env2.reset()["observation"], first)
+
+
+def test_state_roundtrip_and_checkpoint(ug):
+    env_id, n = "UR5DynReach-v1", 3000
+    env = ug.UR5VecEnv(env_id, n, seed=1)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    acts = [torch.rand((n, 6), device="cuda", generator=g) * 2 - 1 for _ in range(30)]
+    for a in acts[:10]:
+        env.step(a)
+    ck = env.state_dict()
+    ref = [tuple(x.clone() if torch.is_tensor(x) else x for x in (env.step(a)[0]["observation"], env.reward)) for a in acts[10:]]
+    env2 = ug.UR5VecEnv(env_id, n, seed=1)
+    env2.load_state_dict(ck)
+    for a, (o, r) in zip(acts[10:], ref):
+        o2 = env2.step(a)[0]["observation"]
+        assert torch.equal(o2, o) and torch.equal(env2.reward, r)
+    for name in ("q", "goal", "obstacle", "obstacle_end", "link_dist", "velocity", "ep_return"):
+        v = torch.randn_like(env.get_state(name))
+        env.set_state(name, v)
+        assert torch.equal(env.get_state(name), v), name
+    with pytest.raises(ug.UrgymError):
+        ug.UR5VecEnv("UR5OriReach-v1", 8).get_state("obstacle")
+
+
+def test_host_buffer_entry_point_matches_device_path(ug):
+    env_id, n = "UR5ObsReach-v1", 5000
+    d_env, h_env = ug.UR5VecEnv(env_id, n, seed=4), ug.UR5VecEnv(env_id, n, seed=4)
+    d_env.reset(); h_env.reset()
+    buf = h_env.alloc_host_buffers()
+    rng = np.random.default_rng(0)
+    for t in range(12):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        buf["actions"].copy_(torch.from_numpy(a))
+        h_env.step_host(buf["actions"], buf)
+        o, r, te, tr, info = d_env.step(torch.from_numpy(a).cuda())
+        assert torch.equal(buf["obs"], o["observation"].cpu()) and torch.equal(buf["reward"], r.cpu())
+        assert torch.equal(buf["terminated"], te.cpu()) and torch.equal(buf["truncated"], tr.cpu())
+        done = (te | tr).bool().cpu()
+        assert torch.equal(buf["terminal_obs"][done], info["terminal_observation"].cpu()[done])
+
+
+@pytest.mark.parametrize("env_id", TASKS)
+def test_gym_style_single_env_matches_oracle(env_id, ug):
+    """demo.py's loop (reset on done) through make()/reset()/step() against one oracle env"""
+    env = ug.make(env_id, render=False, seed=21)
+    orc = oe.make(env_id, geom=oe.GEOM_CAPSULE, stream=oe.PhiloxStream(21), env_index=0, first_event=1)
+    assert env.observation_space["observation"].shape == (ug.UR5VecEnv._FIELDS and env.vec.obs_dim,)
+    assert env.action_space.shape == (6,)
+    event = 2                                    # constructor reset = event 1, explicit reset below = event 2
+    obs, info = env.reset()
+    o2, i2 = orc.reset(event=event)
+    np.testing.assert_allclose(obs["observation"], o2["observation"], atol=1e-5)
+    np.testing.assert_allclose(obs["desired_goal"], o2["desired_goal"], atol=1e-6)
+    rng = np.random.default_rng(0)
+    for t in range(150):
+        a = rng.uniform(-1, 1, 6).astype(np.float32)
+        obs, r, term, trunc, info = env.step(a); event += 1
+        o2, r2, term2, trunc2, info2 = orc.step(a)
+        assert (term, trunc, info["is_success"]) == (term2, trunc2, bool(info2["is_success"]))
+        np.testing.assert_allclose(obs["achieved_goal"][:3], o2["achieved_goal"][:3], atol=1e-5)
+        assert abs(r - r2) <= 1e-5 * max(1.0, abs(r2))
+        # the reference's own API pieces evaluated on the returned arrays
+        assert bool(np.all(env.task.is_success(obs["achieved_goal"], obs["desired_goal"]))) == bool(np.all(orc.task.is_success(o2["achieved_goal"], orc.task.get_goal())))
+        rr = float(np.asarray(env.compute_reward(obs["achieved_goal"], obs["desired_goal"], info)).reshape(-1)[0])
+        assert abs(rr - r2) <= 2e-4 * max(1.0, abs(r2)), (rr, r2)
+        if term or trunc:
+            obs, info = env.reset(); event += 1
+            o2, i2 = orc.reset(event=event)
+            np.testing.assert_allclose(obs["observation"], o2["observation"], atol=1e-5)
+    env.close()
+
+
+def test_injection_protocol_like_model_test(ug):
+    """model_test.py:34-38: reset, inject goal + obstacle, read the observation back, step"""
+    env = ug.make("UR5DynReach-v1", seed=0)
+    orc = oe.make("UR5DynReach-v1", geom=oe.GEOM_CAPSULE, stream=oe.PhiloxStream(0), env_index=0, first_event=1)
+    env.reset(); orc.reset(event=2)
+    data = np.array([0.5, 0.1, 0.1, -2.0, 0.0, -1.0, 0.7, -0.6, 0.4, 1.0, 0.8, 0.0, 0.9, 0.7, 0.6, -2.0, -1.2, 0.0])
+    env.task.set_goal_and_obstacle(data); orc.task.set_goal_and_obstacle(data)
+    np.testing.assert_allclose(env.task.get_obs(), orc.task.get_obs(), atol=1e-5)
+    np.testing.assert_allclose(env.robot.get_obs(), orc.robot.get_obs(), atol=1e-5)
+    np.testing.assert_allclose(env.task.link_dist, orc.task.link_dist, atol=1e-5)
+    rng = np.random.default_rng(1)
+    for t in range(40):
+        a = rng.uniform(-0.3, 0.3, 6).astype(np.float32)
+        o, r, term, trunc, info = env.step(a)
+        o2, r2, term2, trunc2, info2 = orc.step(a)
+        np.testing.assert_allclose(o["observation"], o2["observation"], atol=2e-5)
+        assert abs(r - r2) <= 1e-5 * max(1.0, abs(r2)) and term == term2
+        if term:
+            break
+
+
+def test_c_abi_error_behaviour(ug):
+    L = ug._native.lib()
+    h = ctypes.c_void_p()
+    assert L.urgym_create(ctypes.byref(h), 9, 1, 4, 0, 0, 0) == -1 and b"task" in L.urgym_last_error(None)
+    assert L.urgym_create(ctypes.byref(h), 0, 1, 0, 0, 0, 0) == -1
+    assert L.urgym_create(ctypes.byref(h), 0, 1, 4, 0, 0, 999) == -1
+    assert L.urgym_create(ctypes.byref(h), 0, 1, 4, 0, 0, 0) == 0
+    assert L.urgym_step(h, None, None, None, None, None, None, None, None, None, None, None) == -1
+    assert b"must not be NULL" in L.urgym_last_error(h)
+    assert L.urgym_get_state(h, 2, ctypes.c_void_p(1), None) == -5          # Ori has no obstacle
+    assert L.urgym_destroy(h) == 0

@@ -194,6 +194,11 @@ extern "C" int urgym_set_autoreset(urgym_env_t *h, int enabled) {
     h->autoreset = enabled ? 1 : 0;
     return URGYM_OK;
 }
+extern "C" int urgym_set_seed(urgym_env_t *h, uint64_t seed) {
+    if (!h) return URGYM_EINVAL;
+    h->seed = seed;
+    return URGYM_OK;
+}
 extern "C" int urgym_get_event(const urgym_env_t *h, uint32_t *event) {
     if (!h || !event) return URGYM_EINVAL;
     *event = h->event;

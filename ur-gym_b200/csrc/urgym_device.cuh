@@ -18,8 +18,41 @@
 // instantiation exists so tests/hostcheck can unit-test the very same arithmetic against the oracle on a box
 // without a GPU (it is not linked into liburgym_b200.so's call paths -- there is no CPU fallback).
 #define URGYM_HD __host__ __device__ __forceinline__
+// Out-of-line helpers: the libdevice bodies of sincosf / atan2f (range reduction, slow paths) and the Philox rounds
+// are big; one shared copy each keeps the step kernel's instruction footprint inside the instruction cache (the
+// first profile of the fully inlined kernel -- 13 k SASS instructions -- stalled on instruction fetch).
+#if defined(__CUDACC__)
+#define URGYM_OOL __host__ __device__ __noinline__
+#else
+#define URGYM_OOL __attribute__((noinline))
+#endif
 
 namespace urgym {
+
+// sin / cos of an angle of a few tens of radians at most (joint angles grow by <= 0.1 pi per step for <= 100 steps):
+// two-constant Cody-Waite reduction to [-pi, pi], then the SFU (MUFU.SIN / MUFU.COS, abs error 2^-21.4 on that
+// range = 3.6e-7, i.e. < 1e-6 m at the end of the 1 m chain: inside the 1e-5 m / 1e-5 rad FK tolerance).  About
+// 10 instructions instead of libdevice's ~45 + slow path, and it is called 19 times per env step.
+// The host instantiation (tests/hostcheck) uses libm.
+URGYM_HD void sincos_fast(float x, float *s, float *c) {
+#ifdef __CUDA_ARCH__
+    float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);      // 2 pi rounded to float
+    r = fmaf(-k, -1.7484555e-7f, r);                 // 2 pi - float(2 pi)
+    *s = __sinf(r);
+    *c = __cosf(r);
+#else
+    sincosf(x, s, c);
+#endif
+}
+static URGYM_OOL float atan2_ool(float y, float x) { return atan2f(y, x); }
+URGYM_HD float fdiv(float a, float b) {               // division where 2 ulp are enough (clamped line parameters)
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------ constants
 struct ModelConst {
@@ -28,11 +61,11 @@ struct ModelConst {
     float cap_p0[7][3];         // bounding capsule of each link hull, link frame
     float cap_p1[7][3];
     float cap_m[7];             // capsule margin = bounding radius + hull_margin (so capsule distance <= hull distance)
+    float cap_hl[7];            // half length of the capsule segment (+ round-off allowance), for the sphere broad phase
     int hull_off[8];            // vertex ranges of links 0..6 inside the packed float4 vertex array
     // margins of Bullet's GJK pair detector (distance = |core gap| - marginA - marginB)
     float hull_margin;          // URDF mesh links: 0.001
-    float table_c[3], table_he[3], table_margin;   // core half extents (already shrunk by the margin)
-    float track_c[3], track_he[3], track_margin;
+    float box_c[2][3], box_he[2][3], box_margin[2];    // 0 = table, 1 = track; core half extents (shrunk by the margin)
     float obst_r, obst_h, obst_margin;             // hull mode: cylinder core radius / half height, margin
     float tgt_box_he, tgt_box_margin;              // hull mode: Sta/Dyn target box core
     float tgt_sphere_margin;                       // Obs target sphere: point core, margin = radius
@@ -79,9 +112,9 @@ struct Quat { float x, y, z, w; };
 // pybullet getQuaternionFromEuler(roll,pitch,yaw) = Rz(yaw)Ry(pitch)Rx(roll)          pyb_setup.py:152,313-314
 URGYM_HD Quat quat_from_euler(float roll, float pitch, float yaw) {
     float sr, cr, sp, cp, sy, cy;
-    sincosf(0.5f * roll, &sr, &cr);
-    sincosf(0.5f * pitch, &sp, &cp);
-    sincosf(0.5f * yaw, &sy, &cy);
+    sincos_fast(0.5f * roll, &sr, &cr);
+    sincos_fast(0.5f * pitch, &sp, &cp);
+    sincos_fast(0.5f * yaw, &sy, &cy);
     Quat q;
     q.x = sr * cp * cy - cr * sp * sy;
     q.y = cr * sp * cy + sr * cp * sy;
@@ -103,16 +136,16 @@ URGYM_HD float3 euler_from_quat(Quat q) {
     float sarg = -2.0f * (q.x * q.z - q.w * q.y);
     float3 e;
     if (sarg <= -0.99999f) {
-        e.y = -0.5f * URGYM_PI_F; e.x = 0.0f; e.z = 2.0f * atan2f(q.x, -q.y);
+        e.y = -0.5f * URGYM_PI_F; e.x = 0.0f; e.z = 2.0f * atan2_ool(q.x, -q.y);
     } else if (sarg >= 0.99999f) {
-        e.y = 0.5f * URGYM_PI_F; e.x = 0.0f; e.z = 2.0f * atan2f(-q.x, q.y);
+        e.y = 0.5f * URGYM_PI_F; e.x = 0.0f; e.z = 2.0f * atan2_ool(-q.x, q.y);
     } else {
         // pitch = asin(sarg), evaluated as atan2(sin, cos) with cos(pitch) = |(R21, R22)|: same angle, but not
         // ill-conditioned in FP32 when |pitch| approaches 90 degrees
         float r21 = 2.0f * (q.y * q.z + q.w * q.x), r22 = squ - sqx - sqy + sqz;
-        e.y = atan2f(sarg, sqrtf(r21 * r21 + r22 * r22));
-        e.x = atan2f(r21, r22);
-        e.z = atan2f(2.0f * (q.x * q.y + q.w * q.z), squ + sqx - sqy - sqz);
+        e.y = atan2_ool(sarg, sqrtf(r21 * r21 + r22 * r22));
+        e.x = atan2_ool(r21, r22);
+        e.z = atan2_ool(2.0f * (q.x * q.y + q.w * q.z), squ + sqx - sqy - sqz);
     }
     return e;
 }
@@ -142,10 +175,11 @@ URGYM_HD Quat quat_from_mat(const float *R) {
 // Euler triple of a rotation matrix with PyBullet's formula.  For a unit quaternion
 //   -2(xz-wy) = -R20,  2(yz+wx) = R21,  w2-x2-y2+z2 = R22,  2(xy+wz) = R10,  w2+x2-y2-z2 = R00
 // so the regular branch needs no quaternion; the (rare) gimbal branch goes through quat_from_mat.
+static URGYM_OOL float3 euler_gimbal_ool(const float *R) { return euler_from_quat(quat_from_mat(R)); }
 URGYM_HD float3 euler_from_mat(const float *R) {
     float sarg = -R[6];
-    if (fabsf(sarg) >= 0.99999f) return euler_from_quat(quat_from_mat(R));
-    return f3(atan2f(R[7], R[8]), atan2f(sarg, sqrtf(R[7] * R[7] + R[8] * R[8])), atan2f(R[3], R[0]));
+    if (fabsf(sarg) >= 0.99999f) return euler_gimbal_ool(R);
+    return f3(atan2_ool(R[7], R[8]), atan2_ool(sarg, sqrtf(R[7] * R[7] + R[8] * R[8])), atan2_ool(R[3], R[0]));
 }
 URGYM_HD void mat_from_quat(Quat q, float *R) {
     float n = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w, s = 2.0f / n;
@@ -158,9 +192,9 @@ URGYM_HD void mat_from_quat(Quat q, float *R) {
 // (roll,pitch,yaw), so roll is used as the z angle -- replicated literally)
 URGYM_HD Quat quat_ZYX(float e0, float e1, float e2) {
     float sz, cz, sy, cy, sx, cx;
-    sincosf(0.5f * e0, &sz, &cz);
-    sincosf(0.5f * e1, &sy, &cy);
-    sincosf(0.5f * e2, &sx, &cx);
+    sincos_fast(0.5f * e0, &sz, &cz);
+    sincos_fast(0.5f * e1, &sy, &cy);
+    sincos_fast(0.5f * e2, &sx, &cx);
     Quat q;
     q.x = cz * cy * sx - sz * sy * cx;
     q.y = cz * sy * cx + sz * cy * sx;
@@ -175,7 +209,7 @@ URGYM_HD float angular_distance(Quat a, Quat b) {
     float vx = a.w * b.x - a.x * b.w - a.y * b.z + a.z * b.y;
     float vy = a.w * b.y - a.y * b.w - a.z * b.x + a.x * b.z;
     float vz = a.w * b.z - a.z * b.w - a.x * b.y + a.y * b.x;
-    return 2.0f * atan2f(sqrtf(vx * vx + vy * vy + vz * vz), fabsf(d));
+    return 2.0f * atan2_ool(sqrtf(vx * vx + vy * vy + vz * vz), fabsf(d));
 }
 
 // ------------------------------------------------------------------------------------------------ forward kinematics
@@ -192,7 +226,7 @@ URGYM_HD void fk_advance(const ModelConst &M, Pose &T, int j, float qj) {
         for (int c = 0; c < 3; c++)
             A[3 * r + c] = fmaf(T.R[3 * r], F[c], fmaf(T.R[3 * r + 1], F[3 + c], T.R[3 * r + 2] * F[6 + c]));
     float s, c;
-    sincosf(qj, &s, &c);
+    sincos_fast(qj, &s, &c);
 #pragma unroll
     for (int r = 0; r < 3; r++) {
         T.R[3 * r] = fmaf(A[3 * r], c, A[3 * r + 1] * s);
@@ -225,8 +259,8 @@ URGYM_HD float rsqrt_f(float x) {
     return 1.0f / sqrtf(x);
 #endif
 }
-URGYM_HD uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
+static URGYM_OOL uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll 1
     for (int r = 0; r < 10; r++) {
         if (r) { k.x += 0x9E3779B9u; k.y += 0xBB67AE85u; }
         uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
@@ -457,16 +491,16 @@ URGYM_HD float segseg_dist2(float3 p1, float3 q1, float3 p2, float3 q2) {
     float s, t;
     const float EPS = 1e-12f;
     if (a <= EPS && e <= EPS) { return dot(r, r); }
-    if (a <= EPS) { s = 0.0f; t = clampf(f / e, 0.0f, 1.0f); }
+    if (a <= EPS) { s = 0.0f; t = clampf(fdiv(f, e), 0.0f, 1.0f); }
     else {
         float c = dot(d1, r);
-        if (e <= EPS) { t = 0.0f; s = clampf(-c / a, 0.0f, 1.0f); }
+        if (e <= EPS) { t = 0.0f; s = clampf(fdiv(-c, a), 0.0f, 1.0f); }
         else {
             float b = dot(d1, d2), denom = a * e - b * b;
-            s = denom > EPS * a * e ? clampf((b * f - c * e) / denom, 0.0f, 1.0f) : 0.0f;
-            t = (b * s + f) / e;
-            if (t < 0.0f) { t = 0.0f; s = clampf(-c / a, 0.0f, 1.0f); }
-            else if (t > 1.0f) { t = 1.0f; s = clampf((b - c) / a, 0.0f, 1.0f); }
+            s = denom > EPS * a * e ? clampf(fdiv(b * f - c * e, denom), 0.0f, 1.0f) : 0.0f;
+            t = fdiv(b * s + f, e);
+            if (t < 0.0f) { t = 0.0f; s = clampf(fdiv(-c, a), 0.0f, 1.0f); }
+            else if (t > 1.0f) { t = 1.0f; s = clampf(fdiv(b - c, a), 0.0f, 1.0f); }
         }
     }
     float3 c1 = p1 + s * d1, c2 = p2 + t * d2, dd = c1 - c2;

@@ -100,7 +100,7 @@ URGYM_HD void dyn_twist(const float *start, const float *end, float *vel, Quat &
     float w = clampf(d.w, -1.0f, 1.0f);
     float s2 = 1.0f - d.w * d.w;
     float vn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);      // = sqrt(1 - w^2) for a unit quaternion, better conditioned
-    angle = 2.0f * atan2f(vn, w);                             // = 2 acos(w)
+    angle = 2.0f * atan2_ool(vn, w);                             // = 2 acos(w)
     if (s2 < 10.0f * 1.1920929e-7f || vn == 0.0f) axis = f3(1.0f, 0.0f, 0.0f);
     else axis = (1.0f / vn) * f3(d.x, d.y, d.z);
     vel[0] = (end[0] - start[0]) * 0.5f; vel[1] = (end[1] - start[1]) * 0.5f; vel[2] = (end[2] - start[2]) * 0.5f;
@@ -111,7 +111,7 @@ URGYM_HD ObstW obstacle_dyn(const float *start, const float *vel, Quat qs, float
     float t = (float)moved * URGYM_DT_ENV;
     O.c = f3(start[0] + t * vel[0], start[1] + t * vel[1], start[2] + t * vel[2]);
     float s, c;
-    sincosf(0.25f * t * angle, &s, &c);          // half of the rotated angle t * (angle / 2)
+    sincos_fast(0.25f * t * angle, &s, &c);          // half of the rotated angle t * (angle / 2)
     Quat r; r.x = axis.x * s; r.y = axis.y * s; r.z = axis.z * s; r.w = c;
     O.q = quat_mul(r, qs);                        // world-frame increment on the left
     O.u = quat_axis_z(O.q);
@@ -138,7 +138,7 @@ URGYM_HD float seg_box_dist2(float3 a, float3 b, float3 c, float3 he) {
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         if (dd[i] != 0.0f) {
-            float inv = 1.0f / dd[i];
+            float inv = fdiv(1.0f, dd[i]);
 #pragma unroll
             for (int sgn = 0; sgn < 2; sgn++) {
                 float t = ((sgn ? hh[i] : -hh[i]) - pp[i]) * inv;
@@ -149,70 +149,73 @@ URGYM_HD float seg_box_dist2(float3 a, float3 b, float3 c, float3 he) {
             }
         }
     }
-    float t = (ghi > glo) ? lo + (hi - lo) * (-glo / (ghi - glo)) : lo;
+    float t = (ghi > glo) ? lo + (hi - lo) * fdiv(-glo, ghi - glo) : lo;
     return d2(t);
 }
 URGYM_HD float point_seg_dist2(float3 p, float3 a, float3 b) {
     float3 ab = b - a, ap = p - a;
     float den = dot(ab, ab);
-    float t = den > 0.0f ? clampf(dot(ap, ab) / den, 0.0f, 1.0f) : 0.0f;
+    float t = den > 0.0f ? clampf(fdiv(dot(ap, ab), den), 0.0f, 1.0f) : 0.0f;
     float3 e = ap - t * ab;
     return dot(e, e);
 }
 
-// World-space collision view of the robot.  Links are PyBullet link indices 1..6 (slot l-1).
-template <int GEOM> struct RobotGeom;
+// Collision shape of ONE link in the world.  The step walks the chain once (a rolled loop over the links: the code
+// of one iteration stays resident in the instruction cache) and tests each link as soon as its pose is known, so only
+// the shapes of links 1..3 (the first members of the self-collision pairs) are kept.
+template <int GEOM> struct LinkShape;
 
-template <> struct RobotGeom<GEOM_CAPSULE> {
-    float3 a[6], b[6];
-    const float4 *hv;     // unused
-    URGYM_HD void set_link(const ModelConst &M, int l, const Pose &T) {
-        a[l - 1] = T.p + rot(T.R, f3(M.cap_p0[l][0], M.cap_p0[l][1], M.cap_p0[l][2]));
-        b[l - 1] = T.p + rot(T.R, f3(M.cap_p1[l][0], M.cap_p1[l][1], M.cap_p1[l][2]));
+template <> struct LinkShape<GEOM_CAPSULE> {
+    float3 a, b;            // capsule segment
+    URGYM_HD void set(const ModelConst &M, int l, const Pose &T, const float4 *) {
+        a = T.p + rot(T.R, f3(M.cap_p0[l][0], M.cap_p0[l][1], M.cap_p0[l][2]));
+        b = T.p + rot(T.R, f3(M.cap_p1[l][0], M.cap_p1[l][1], M.cap_p1[l][2]));
     }
-    URGYM_HD void set_neutral(const ModelConst &M) {
-#pragma unroll
-        for (int l = 1; l < 7; l++) {
-            a[l - 1] = f3(M.neutral_ca[l][0], M.neutral_ca[l][1], M.neutral_ca[l][2]);
-            b[l - 1] = f3(M.neutral_cb[l][0], M.neutral_cb[l][1], M.neutral_cb[l][2]);
-        }
+    URGYM_HD void set_neutral(const ModelConst &M, int l, const float4 *) {
+        a = f3(M.neutral_ca[l][0], M.neutral_ca[l][1], M.neutral_ca[l][2]);
+        b = f3(M.neutral_cb[l][0], M.neutral_cb[l][1], M.neutral_cb[l][2]);
     }
     // getClosestPoints(UR5, obstacle, linkIndexA=l)[0][8]                              pyb_setup.py:439-456
     URGYM_HD float obstacle_dist(const ModelConst &M, int l, const ObstW &O) const {
         float3 oa = O.c - M.obst_cap_h * O.u, ob = O.c + M.obst_cap_h * O.u;
-        return sqrtf(segseg_dist2(a[l - 1], b[l - 1], oa, ob)) - M.cap_m[l] - M.obst_cap_m;
+        return sqrtf(segseg_dist2(a, b, oa, ob)) - M.cap_m[l] - M.obst_cap_m;
     }
-    URGYM_HD bool box_hit(const ModelConst &M, int l, const float *c, const float *he, float margin) const {
+    // box 0 = table, 1 = track
+    URGYM_HD bool box_hit(const ModelConst &M, int l, int box) const {
+        float margin = M.box_margin[box];
         float reach = URGYM_COLLISION_MARGIN + M.cap_m[l] + margin;
-        float3 bc = f3(c[0], c[1], c[2]), bh = f3(he[0], he[1], he[2]);
-        if (seg_box_lower2(a[l - 1], b[l - 1], bc, bh) > reach * reach) return false;      // broad phase (exact bound)
-        return sqrtf(seg_box_dist2(a[l - 1], b[l - 1], bc, bh)) - M.cap_m[l] - margin <= URGYM_COLLISION_MARGIN;
+        float3 bc = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
+        float3 bh = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
+        if (seg_box_lower2(a, b, bc, bh) > reach * reach) return false;      // broad phase (exact bound)
+        return sqrtf(seg_box_dist2(a, b, bc, bh)) - M.cap_m[l] - margin <= URGYM_COLLISION_MARGIN;
     }
-    URGYM_HD bool self_hit(const ModelConst &M, int l1, int l2) const {
-        return sqrtf(segseg_dist2(a[l1 - 1], b[l1 - 1], a[l2 - 1], b[l2 - 1])) - M.cap_m[l1] - M.cap_m[l2] <=
-               URGYM_COLLISION_MARGIN;
+    URGYM_HD bool link_hit(const ModelConst &M, int l, int l2, const LinkShape &o) const {
+        float reach = URGYM_COLLISION_MARGIN + M.cap_m[l] + M.cap_m[l2];
+        // broad phase (exact bound): segments live inside the spheres about their midpoints
+        float3 dm = 0.5f * ((a + b) - (o.a + o.b));
+        float far = reach + M.cap_hl[l] + M.cap_hl[l2];
+        if (dot(dm, dm) > far * far) return false;
+        return segseg_dist2(a, b, o.a, o.b) <= reach * reach;
     }
 };
 
 // the reference's geometry: convex hulls of the collision meshes, cylinder obstacle, GJK with Bullet's margins.
 // The bounding capsules serve as an exact-safe broad phase for the collision booleans (capsule distance is a lower
-// bound of the hull distance), the hull GJK runs only where the capsule bound cannot decide.
-template <> struct RobotGeom<GEOM_HULL> {
-    Pose T[6];
-    RobotGeom<GEOM_CAPSULE> cap;
-    const float4 *hv;     // packed hull vertices (shared memory on the device)
-    URGYM_HD void set_link(const ModelConst &M, int l, const Pose &P) { T[l - 1] = P; cap.set_link(M, l, P); }
-    URGYM_HD void set_neutral(const ModelConst &M) {
-        cap.set_neutral(M);
+// bound of the hull distance); the hull GJK runs only where the capsule bound cannot decide.
+template <> struct LinkShape<GEOM_HULL> {
+    Pose T;
+    LinkShape<GEOM_CAPSULE> cap;
+    const float4 *hv;       // packed hull vertices (shared memory on the device)
+    URGYM_HD void set(const ModelConst &M, int l, const Pose &P, const float4 *verts) { T = P; hv = verts; cap.set(M, l, P, verts); }
+    URGYM_HD void set_neutral(const ModelConst &M, int l, const float4 *verts) {
+        hv = verts;
+        cap.set_neutral(M, l, verts);
 #pragma unroll
-        for (int l = 1; l < 7; l++) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) T[l - 1].R[k] = M.neutral_R[l][k];
-            T[l - 1].p = f3(M.neutral_p[l][0], M.neutral_p[l][1], M.neutral_p[l][2]);
-        }
+        for (int k = 0; k < 9; k++) T.R[k] = M.neutral_R[l][k];
+        T.p = f3(M.neutral_p[l][0], M.neutral_p[l][1], M.neutral_p[l][2]);
     }
     URGYM_HD HullW hull(const ModelConst &M, int l) const {
-        HullW H; H.v = hv + M.hull_off[l]; H.n = M.hull_off[l + 1] - M.hull_off[l]; H.T = &T[l - 1];
+        HullW H; H.v = hv + M.hull_off[l]; H.n = M.hull_off[l + 1] - M.hull_off[l]; H.T = &T;
         return H;
     }
     URGYM_HD float obstacle_dist(const ModelConst &M, int l, const ObstW &O) const {
@@ -230,17 +233,18 @@ template <> struct RobotGeom<GEOM_HULL> {
         float d = gjk_distance(hull(M, l), C, deep);
         return d - M.hull_margin - M.obst_margin;
     }
-    URGYM_HD bool box_hit(const ModelConst &M, int l, const float *c, const float *he, float margin) const {
-        if (!cap.box_hit(M, l, c, he, margin)) return false;
-        BoxA B; B.c = f3(c[0], c[1], c[2]); B.he = f3(he[0], he[1], he[2]);
+    URGYM_HD bool box_hit(const ModelConst &M, int l, int box) const {
+        if (!cap.box_hit(M, l, box)) return false;
+        BoxA B; B.c = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
+        B.he = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
         bool deep;
         float d = gjk_distance(hull(M, l), B, deep);
-        return d - M.hull_margin - margin <= URGYM_COLLISION_MARGIN;
+        return d - M.hull_margin - M.box_margin[box] <= URGYM_COLLISION_MARGIN;
     }
-    URGYM_HD bool self_hit(const ModelConst &M, int l1, int l2) const {
-        if (!cap.self_hit(M, l1, l2)) return false;
+    URGYM_HD bool link_hit(const ModelConst &M, int l, int l2, const LinkShape &o) const {
+        if (!cap.link_hit(M, l, l2, o.cap)) return false;
         bool deep;
-        float d = gjk_distance(hull(M, l1), hull(M, l2), deep);
+        float d = gjk_distance(hull(M, l), o.hull(M, l2), deep);
         return d - 2.0f * M.hull_margin <= URGYM_COLLISION_MARGIN;
     }
 };
@@ -262,42 +266,42 @@ URGYM_HD float target_obstacle_dist(const ModelConst &M, const float *goal, cons
     return d - M.tgt_box_margin - M.obst_margin;
 }
 
-// PyBullet.check_collision  pyb_setup.py:382-429 (same pairs; the early-out order does not change the boolean).
-// dist[5] receives the link 2..6 <-> obstacle distances (the values get_link_distances would return).
+// Forward kinematics + PyBullet.check_collision (pyb_setup.py:382-429) + get_link_distances (pyb_setup.py:439-456) in
+// one pass over the chain.  Same pairs as the reference (the early-out order does not change the boolean):
+//   links 2..6 vs obstacle (when keys[5] == 'obstacle'), links 2..6 vs table and track,
+//   self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6).
+// ee[6] = EE position + PyBullet Euler triple (UR5.py:320-325,334-340); d0..d4 = link 2..6 <-> obstacle distances.
+// q is read through `qrow` (memory, e.g. the joint columns of the observation row) so the loop can stay rolled.
 template <int TASK, int GEOM>
-URGYM_HD bool check_collision(const ModelConst &M, const RobotGeom<GEOM> &Rg, const ObstW &O, float *dist) {
-    bool hit = false;
-    if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
-#pragma unroll
-        for (int l = 2; l < 7; l++) {
-            dist[l - 2] = Rg.obstacle_dist(M, l, O);
-            hit = hit || (dist[l - 2] <= URGYM_COLLISION_MARGIN);
-        }
-    }
-#pragma unroll
-    for (int l = 2; l < 7; l++) {
-        hit = hit || Rg.box_hit(M, l, M.table_c, M.table_he, M.table_margin);
-        hit = hit || Rg.box_hit(M, l, M.track_c, M.track_he, M.track_margin);
-    }
-    hit = hit || Rg.self_hit(M, 1, 3) || Rg.self_hit(M, 1, 4) || Rg.self_hit(M, 1, 5) || Rg.self_hit(M, 1, 6);
-    hit = hit || Rg.self_hit(M, 2, 4) || Rg.self_hit(M, 2, 5) || Rg.self_hit(M, 2, 6);
-    hit = hit || Rg.self_hit(M, 3, 5) || Rg.self_hit(M, 3, 6);
-    return hit;
-}
-
-// ------------------------------------------------------------------------------------------------ observation
-// forward kinematics + collision view.  ee[6] = EE position + PyBullet Euler triple (UR5.py:320-325,334-340)
-template <int GEOM>
-URGYM_HD void robot_view(const ModelConst &M, const float *q, float *ee, RobotGeom<GEOM> &Rg) {
+URGYM_HD bool robot_pass(const ModelConst &M, const float *qrow, const ObstW &O, const float4 *hv, bool collide,
+                         float *ee, float &d0, float &d1, float &d2, float &d3, float &d4) {
     Pose T;
     pose_identity(T);
-#pragma unroll
+    LinkShape<GEOM> s1, s2, s3, cur;
+    bool hit = false;
+#pragma unroll 1
     for (int l = 1; l < 7; l++) {
-        fk_advance(M, T, l - 1, q[l - 1]);
-        Rg.set_link(M, l, T);
+        fk_advance(M, T, l - 1, qrow[l - 1]);
+        if (collide) {
+            cur.set(M, l, T, hv);
+            if (l >= 2) {
+                if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
+                    float d = cur.obstacle_dist(M, l, O);
+                    hit = hit || (d <= URGYM_COLLISION_MARGIN);
+                    if (l == 2) d0 = d; else if (l == 3) d1 = d; else if (l == 4) d2 = d; else if (l == 5) d3 = d; else d4 = d;
+                }
+#pragma unroll 1
+                for (int box = 0; box < 2; box++) hit = hit || cur.box_hit(M, l, box);
+            }
+            if (l >= 3) hit = hit || cur.link_hit(M, l, 1, s1);
+            if (l >= 4) hit = hit || cur.link_hit(M, l, 2, s2);
+            if (l >= 5) hit = hit || cur.link_hit(M, l, 3, s3);
+            if (l == 1) s1 = cur; else if (l == 2) s2 = cur; else if (l == 3) s3 = cur;
+        }
     }
     float3 e = euler_from_mat(T.R);
     ee[0] = T.p.x; ee[1] = T.p.y; ee[2] = T.p.z; ee[3] = e.x; ee[4] = e.y; ee[5] = e.z;
+    return hit;
 }
 
 // task part of the observation   reach.py:189-190 (Ori), 307-308 (Obs), 454-458 (Sta), 653-657 (Dyn)
@@ -376,11 +380,10 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
         O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
     }
     // 3. FK and collision                                                                      core.py:310
-    RobotGeom<GEOM> Rg;
-    Rg.hv = hv;
     float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    robot_view<GEOM>(M, s.q, ee, Rg);
-    bool coll = check_collision<TASK, GEOM>(M, Rg, O, dist);
+#pragma unroll
+    for (int k = 0; k < 6; k++) row[6 + k] = s.q[k];
+    bool coll = robot_pass<TASK, GEOM>(M, row + 6, O, hv, true, ee, dist[0], dist[1], dist[2], dist[3], dist[4]);
     // 4. observation: carries link_dist from BEFORE this step's reward (quirk Q1)               core.py:311
     write_obs_row<TASK>(row, ee, s.q, s.E, O, vel, s.ld);
     // 5. termination                                                                           core.py:313-315
@@ -443,10 +446,10 @@ URGYM_HD void env_observe(const ModelConst &M, const EnvState &s, const float *s
     } else {
         O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
     }
-    RobotGeom<GEOM_CAPSULE> Rg;     // only the EE pose is needed
-    Rg.hv = nullptr;
-    float ee[6];
-    robot_view<GEOM_CAPSULE>(M, s.q, ee, Rg);
+    float ee[6], du[5];
+#pragma unroll
+    for (int k = 0; k < 6; k++) row[6 + k] = s.q[k];
+    robot_pass<TASK, GEOM_CAPSULE>(M, row + 6, O, nullptr, false, ee, du[0], du[1], du[2], du[3], du[4]);   // EE pose only
     write_obs_row<TASK>(row, ee, s.q, s.E, O, vel, s.ld);
 }
 
@@ -465,11 +468,8 @@ URGYM_HD bool env_refresh(const ModelConst &M, EnvState &s, const float4 *hv) {
     } else {
         O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
     }
-    RobotGeom<GEOM> Rg;
-    Rg.hv = hv;
     float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    robot_view<GEOM>(M, s.q, ee, Rg);
-    bool coll = check_collision<TASK, GEOM>(M, Rg, O, dist);
+    bool coll = robot_pass<TASK, GEOM>(M, s.q, O, hv, true, ee, dist[0], dist[1], dist[2], dist[3], dist[4]);
     if (TT::HAS_OBST) {
 #pragma unroll
         for (int k = 0; k < 5; k++) s.ld[k] = dist[k];
@@ -561,11 +561,13 @@ URGYM_HD int env_reset(const ModelConst &M, EnvState &s, ResetStream rs, const f
     ObstW O;
     if (TT::HAS_OBST) {
         O = obstacle_static(&s.E[TT::OBST]);           // Dyn: obstacle placed at START after sampling   reach.py:678
-        RobotGeom<GEOM> Rg;
-        Rg.hv = hv;
-        Rg.set_neutral(M);
-#pragma unroll
-        for (int l = 2; l < 7; l++) s.ld[l - 2] = Rg.obstacle_dist(M, l, O);        // reach.py:323-324,478-479,680-681
+#pragma unroll 1
+        for (int l = 2; l < 7; l++) {                   // reach.py:323-324,478-479,680-681
+            LinkShape<GEOM> L;
+            L.set_neutral(M, l, hv);
+            float d = L.obstacle_dist(M, l, O);
+            if (l == 2) s.ld[0] = d; else if (l == 3) s.ld[1] = d; else if (l == 4) s.ld[2] = d; else if (l == 5) s.ld[3] = d; else s.ld[4] = d;
+        }
     } else {
         O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
 #pragma unroll

@@ -42,6 +42,9 @@ static void build_model_const(ModelConst &M) {
             M.cap_p1[l][k] = (float)UR5E_CAPSULE_P1[3 * l + k];
         }
         M.cap_m[l] = (float)(UR5E_CAPSULE_R[l] + hull_margin);
+        double hl = 0.0;
+        for (int k = 0; k < 3; k++) hl += (UR5E_CAPSULE_P1[3 * l + k] - UR5E_CAPSULE_P0[3 * l + k]) * (UR5E_CAPSULE_P1[3 * l + k] - UR5E_CAPSULE_P0[3 * l + k]);
+        M.cap_hl[l] = (float)(0.5 * sqrt(hl) + 1e-5);
     }
     for (int l = 0; l < 8; l++) M.hull_off[l] = UR5E_HULL_OFFSET[l];
     M.hull_margin = (float)hull_margin;
@@ -51,10 +54,10 @@ static void build_model_const(ModelConst &M) {
     // create_track(0.2, 1.1, 0.12, x_offset=0, z_offset=0)         reach.py:170; pyb_setup.py:835-844
     const double kc[3] = {0.0, 0.0, -0.06}, kh[3] = {0.1, 0.55, 0.06};
     for (int k = 0; k < 3; k++) {
-        M.table_c[k] = (float)tc[k]; M.table_he[k] = (float)(th[k] - pm);
-        M.track_c[k] = (float)kc[k]; M.track_he[k] = (float)(kh[k] - pm);
+        M.box_c[0][k] = (float)tc[k]; M.box_he[0][k] = (float)(th[k] - pm);
+        M.box_c[1][k] = (float)kc[k]; M.box_he[1][k] = (float)(kh[k] - pm);
     }
-    M.table_margin = M.track_margin = (float)pm;
+    M.box_margin[0] = M.box_margin[1] = (float)pm;
     // obstacle cylinder radius 0.05, height 0.4                    reach.py:279-283,427-431,626-630
     M.obst_r = (float)(0.05 - pm); M.obst_h = (float)(0.2 - pm); M.obst_margin = (float)pm;
     M.tgt_box_he = (float)(0.025 - pm); M.tgt_box_margin = (float)pm;   // reach.py:418-426
