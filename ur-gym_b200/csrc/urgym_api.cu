@@ -75,7 +75,8 @@ struct urgym_env {
     int task, geom, device;
     int64_t n, offset;
     uint64_t seed;
-    uint32_t event;         // reset-event counter: position of the counter-based reset stream
+    uint32_t *d_event;      // device-resident reset-event counter: position of the counter-based reset stream.
+                            // It lives on the device so that a captured CUDA graph of steps advances it on replay.
     int autoreset;
     StateView st;
     ModelConst model;
@@ -112,6 +113,24 @@ extern "C" int64_t urgym_num_envs(const urgym_env_t *h) { return h ? h->n : 0; }
 extern "C" const char *urgym_last_error(const urgym_env_t *h) { return h ? h->err : g_create_err; }
 extern "C" int64_t urgym_launch_count(const urgym_env_t *h) { return h ? h->launches : 0; }
 
+static inline uint2 key_of(uint64_t seed) { return make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)); }
+
+// [geom][task]
+static const step_launcher_t k_step[2][4] = {
+    {urgym_inst_step_0_0, urgym_inst_step_1_0, urgym_inst_step_2_0, urgym_inst_step_3_0},
+    {urgym_inst_step_0_1, urgym_inst_step_1_1, urgym_inst_step_2_1, urgym_inst_step_3_1}};
+static const aux_launcher_t k_reset[2][4] = {
+    {urgym_inst_reset_0_0, urgym_inst_reset_1_0, urgym_inst_reset_2_0, urgym_inst_reset_3_0},
+    {urgym_inst_reset_0_1, urgym_inst_reset_1_1, urgym_inst_reset_2_1, urgym_inst_reset_3_1}};
+static const aux_launcher_t k_refresh[2][4] = {
+    {urgym_inst_refresh_0_0, urgym_inst_refresh_1_0, urgym_inst_refresh_2_0, urgym_inst_refresh_3_0},
+    {urgym_inst_refresh_0_1, urgym_inst_refresh_1_1, urgym_inst_refresh_2_1, urgym_inst_refresh_3_1}};
+static const aux_launcher_t k_observe[4] = {launch_observe<0>, launch_observe<1>, launch_observe<2>, launch_observe<3>};
+
+static const aux_launcher_t k_prepare[2][4] = {
+    {urgym_inst_prepare_0_0, urgym_inst_prepare_1_0, urgym_inst_prepare_2_0, urgym_inst_prepare_3_0},
+    {urgym_inst_prepare_0_1, urgym_inst_prepare_1_1, urgym_inst_prepare_2_1, urgym_inst_prepare_3_1}};
+
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_envs, int64_t env_index_offset,
@@ -144,7 +163,7 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
         // planes: 16-byte groups first, all 256-byte aligned
         const size_t n = (size_t)n_envs;
         const size_t p16 = align_up(n * 16, 256), p8 = align_up(n * 8, 256), p4 = align_up(n * 4, 256);
-        const size_t total = 3 * p16 + p4 + 4 * p16 + p8 + p4 + p16 + p8 + URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8;
+        const size_t total = 3 * p16 + p4 + 4 * p16 + p8 + p4 + p16 + p8 + URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8 + 256;
         if ((e = cudaMalloc(&h->pool, total)) != cudaSuccess) { rc = URGYM_ENOMEM; break; }
         if ((e = cudaMemset(h->pool, 0, total)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
         char *p = (char *)h->pool;
@@ -157,7 +176,13 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
         h->st.e1 = (float *)p; p += p4;
         h->st.va = (float4 *)p; p += p16;
         h->st.vb = (float2 *)p; p += p8;
-        h->stats = (unsigned long long *)p;
+        h->stats = (unsigned long long *)p; p += URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8;
+        h->d_event = (uint32_t *)p;
+        {
+            AuxArgs dummy;
+            memset(&dummy, 0, sizeof(dummy));
+            if ((e = k_prepare[geom][task](h->model, dummy, 0)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
+        }
         if (geom == URGYM_GEOM_HULL) {
             static float4 hv[UR5E_NUM_HULL_VERTS];
             for (int i = 0; i < UR5E_NUM_HULL_VERTS; i++)
@@ -199,30 +224,21 @@ extern "C" int urgym_set_seed(urgym_env_t *h, uint64_t seed) {
     h->seed = seed;
     return URGYM_OK;
 }
-extern "C" int urgym_get_event(const urgym_env_t *h, uint32_t *event) {
+extern "C" int urgym_get_event(const urgym_env_t *hc, uint32_t *event) {
+    urgym_env *h = const_cast<urgym_env *>(hc);
     if (!h || !event) return URGYM_EINVAL;
-    *event = h->event;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(event, h->d_event, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return URGYM_OK;
 }
 extern "C" int urgym_set_event(urgym_env_t *h, uint32_t event) {
     if (!h) return URGYM_EINVAL;
-    h->event = event;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h->d_event, &event, sizeof(uint32_t), cudaMemcpyHostToDevice));
     return URGYM_OK;
 }
-
-static inline uint2 key_of(uint64_t seed) { return make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)); }
-
-// [geom][task]
-static const step_launcher_t k_step[2][4] = {
-    {urgym_inst_step_0_0, urgym_inst_step_1_0, urgym_inst_step_2_0, urgym_inst_step_3_0},
-    {urgym_inst_step_0_1, urgym_inst_step_1_1, urgym_inst_step_2_1, urgym_inst_step_3_1}};
-static const aux_launcher_t k_reset[2][4] = {
-    {urgym_inst_reset_0_0, urgym_inst_reset_1_0, urgym_inst_reset_2_0, urgym_inst_reset_3_0},
-    {urgym_inst_reset_0_1, urgym_inst_reset_1_1, urgym_inst_reset_2_1, urgym_inst_reset_3_1}};
-static const aux_launcher_t k_refresh[2][4] = {
-    {urgym_inst_refresh_0_0, urgym_inst_refresh_1_0, urgym_inst_refresh_2_0, urgym_inst_refresh_3_0},
-    {urgym_inst_refresh_0_1, urgym_inst_refresh_1_1, urgym_inst_refresh_2_1, urgym_inst_refresh_3_1}};
-static const aux_launcher_t k_observe[4] = {launch_observe<0>, launch_observe<1>, launch_observe<2>, launch_observe<3>};
 
 extern "C" int urgym_step(urgym_env_t *h, const float *actions, float *obs, float *achieved, float *desired,
                           float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
@@ -232,14 +248,23 @@ extern "C" int urgym_step(urgym_env_t *h, const float *actions, float *obs, floa
         return fail(h, URGYM_EINVAL, "urgym_step: actions, obs, reward, terminated, truncated, is_success must not be NULL%s", "");
     CK(cudaSetDevice(h->device));
     StepArgs A;
-    A.st = h->st; A.n = h->n; A.offset = h->offset; A.key = key_of(h->seed);
-    A.event = ++h->event;
-    A.autoreset = h->autoreset;
+    A.st = h->st; A.n = h->n;
     A.actions = actions; A.obs = obs; A.ach = achieved; A.des = desired; A.rew = reward;
-    A.term = terminated; A.trunc = truncated; A.succ = is_success; A.tobs = terminal_obs; A.tach = terminal_achieved;
-    A.stats = h->stats; A.hull = h->hull;
+    A.term = terminated; A.trunc = truncated; A.succ = is_success;
+    A.stats = h->stats; A.event = h->d_event; A.hull = h->hull;
     CK(k_step[h->geom][h->task](h->model, A, (cudaStream_t)stream));
     h->launches++;
+    if (h->autoreset) {
+        // the finished envs (terminated | truncated) restart in a second, dense kernel
+        AuxArgs R;
+        memset(&R, 0, sizeof(R));
+        R.st = h->st; R.n = h->n; R.offset = h->offset; R.key = key_of(h->seed);
+        R.mask = terminated; R.mask2 = truncated; R.autoreset = 1;
+        R.obs = obs; R.ach = achieved; R.des = desired; R.tobs = terminal_obs; R.tach = terminal_achieved;
+        R.stats = h->stats; R.event = h->d_event; R.hull = h->hull;
+        CK(k_reset[h->geom][h->task](h->model, R, (cudaStream_t)stream));
+        h->launches++;
+    }
     return URGYM_OK;
 }
 
@@ -249,8 +274,10 @@ extern "C" int urgym_reset(urgym_env_t *h, const uint8_t *mask, float *obs, floa
     AuxArgs A;
     memset(&A, 0, sizeof(A));
     A.st = h->st; A.n = h->n; A.offset = h->offset; A.key = key_of(h->seed);
-    A.event = ++h->event;
-    A.mask = mask; A.obs = obs; A.ach = achieved; A.des = desired; A.stats = h->stats; A.hull = h->hull;
+    A.mask = mask; A.obs = obs; A.ach = achieved; A.des = desired; A.stats = h->stats; A.event = h->d_event; A.hull = h->hull;
+    urgym_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_event);       // an explicit reset is a reset event of its own
+    CK(cudaGetLastError());
+    h->launches++;
     CK(k_reset[h->geom][h->task](h->model, A, (cudaStream_t)stream));
     h->launches++;
     return URGYM_OK;

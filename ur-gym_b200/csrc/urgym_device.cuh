@@ -46,6 +46,20 @@ URGYM_HD void sincos_fast(float x, float *s, float *c) {
 #endif
 }
 static URGYM_OOL float atan2_ool(float y, float x) { return atan2f(y, x); }
+URGYM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+URGYM_HD float rsqrt_f(float x) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
 URGYM_HD float fdiv(float a, float b) {               // division where 2 ulp are enough (clamped line parameters)
 #ifdef __CUDA_ARCH__
     return __fdividef(a, b);
@@ -172,14 +186,16 @@ URGYM_HD Quat quat_from_mat(const float *R) {
     }
     return q;
 }
-// Euler triple of a rotation matrix with PyBullet's formula.  For a unit quaternion
-//   -2(xz-wy) = -R20,  2(yz+wx) = R21,  w2-x2-y2+z2 = R22,  2(xy+wz) = R10,  w2+x2-y2-z2 = R00
-// so the regular branch needs no quaternion; the (rare) gimbal branch goes through quat_from_mat.
-static URGYM_OOL float3 euler_gimbal_ool(const float *R) { return euler_from_quat(quat_from_mat(R)); }
+// Euler triple of a rotation matrix the way PyBullet produces it: matrix -> quaternion (btMatrix3x3::getRotation)
+// -> getEulerFromQuaternion.  The quaternion is normalised on the way: an FP32 chain product is orthonormal only to
+// a few 1e-7, and reading roll and yaw from different entries of such a matrix amplifies that defect by
+// 1/cos(pitch) near gimbal lock; a unit quaternion is an exact rotation, so the triple always encodes a rotation
+// within round-off of the true one.
 URGYM_HD float3 euler_from_mat(const float *R) {
-    float sarg = -R[6];
-    if (fabsf(sarg) >= 0.99999f) return euler_gimbal_ool(R);
-    return f3(atan2_ool(R[7], R[8]), atan2_ool(sarg, sqrtf(R[7] * R[7] + R[8] * R[8])), atan2_ool(R[3], R[0]));
+    Quat q = quat_from_mat(R);
+    float n = rsqrt_f(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    q.x *= n; q.y *= n; q.z *= n; q.w *= n;
+    return euler_from_quat(q);
 }
 URGYM_HD void mat_from_quat(Quat q, float *R) {
     float n = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w, s = 2.0f / n;
@@ -245,20 +261,6 @@ URGYM_HD void fk_link(const ModelConst &M, const float *q, int link, Pose &T) {
 }
 
 // ------------------------------------------------------------------------------------------------ Philox4x32-10
-URGYM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
-#ifdef __CUDA_ARCH__
-    return __umulhi(a, b);
-#else
-    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
-#endif
-}
-URGYM_HD float rsqrt_f(float x) {
-#ifdef __CUDA_ARCH__
-    return rsqrtf(x);
-#else
-    return 1.0f / sqrtf(x);
-#endif
-}
 static URGYM_OOL uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll 1
     for (int r = 0; r < 10; r++) {

@@ -489,15 +489,30 @@ struct Draws {
 };
 URGYM_HD float lerp_u(float lo, float hi, float u) { return lo + (hi - lo) * u; }     // np_random.uniform(low, high)
 
+// ReachDyn's cheap half of the rejection rule for iteration rs.iter: d(obstacle_end, obstacle_start) >= 1 m
+// (reach.py:674-675).  Only ~17.5 % of the draws pass, so the auto-reset kernel searches iterations in parallel
+// with this test before the full sample is evaluated.
+URGYM_HD bool dyn_pair_far_enough(const ResetStream &rs) {
+    float3 olo, ohi;
+    obstacle_range<TASK_DYN>(olo, ohi);
+    Draws D;
+    D.b[0] = rs.block(0); D.b[1] = rs.block(1);
+    float dx = lerp_u(olo.x, ohi.x, D.u(3)) - lerp_u(olo.x, ohi.x, D.u(0));
+    float dy = lerp_u(olo.y, ohi.y, D.u(4)) - lerp_u(olo.y, ohi.y, D.u(1));
+    float dz = lerp_u(olo.z, ohi.z, D.u(5)) - lerp_u(olo.z, ohi.z, D.u(2));
+    return !(sqrtf(dx * dx + dy * dy + dz * dz) < 1.0f);
+}
+
 // Reach*.reset (reach.py:197-200,313-326,465-481,664-683) with _sample_goal / _sample_obstacle
 // (reach.py:206-210,337-346,505-516,715-726): fills E, returns the number of rejection iterations used.
+// k_start: the first rejection iteration to look at (the caller may already know that earlier ones fail).
 template <int TASK, int GEOM>
-URGYM_HD int sample_episode(const ModelConst &M, ResetStream rs, float *E) {
+URGYM_HD int sample_episode(const ModelConst &M, ResetStream rs, float *E, int k_start = 0) {
     typedef Traits<TASK> TT;
     float3 glo, ghi, olo, ohi;
     goal_range<TASK>(glo, ghi);
     obstacle_range<TASK>(olo, ohi);
-    int k = 0;
+    int k = k_start;
     for (;;) {
         rs.iter = (uint32_t)k;
         Draws D;
@@ -551,9 +566,9 @@ URGYM_HD int sample_episode(const ModelConst &M, ResetStream rs, float *E) {
 // pose, first observation.  The velocity columns of `row` are left untouched (quirk Q4: the caller puts the
 // previous ReachDyn.velocity there).  Returns the rejection iterations used.
 template <int TASK, int GEOM>
-URGYM_HD int env_reset(const ModelConst &M, EnvState &s, ResetStream rs, const float4 *hv, float *row) {
+URGYM_HD int env_reset(const ModelConst &M, EnvState &s, ResetStream rs, const float4 *hv, float *row, int k_start = 0) {
     typedef Traits<TASK> TT;
-    int iters = sample_episode<TASK, GEOM>(M, rs, s.E);
+    int iters = sample_episode<TASK, GEOM>(M, rs, s.E, k_start);
 #pragma unroll
     for (int j = 0; j < 6; j++) s.q[j] = M.neutral_q[j];
     s.elapsed = 0;

@@ -16,3 +16,6 @@ cudaError_t NAME(urgym_inst_reset_, URGYM_INST_TASK, URGYM_INST_GEOM)(const Mode
 cudaError_t NAME(urgym_inst_refresh_, URGYM_INST_TASK, URGYM_INST_GEOM)(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     return launch_refresh<URGYM_INST_TASK, URGYM_INST_GEOM>(M, A, s);
 }
+cudaError_t NAME(urgym_inst_prepare_, URGYM_INST_TASK, URGYM_INST_GEOM)(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
+    return prepare_kernels<URGYM_INST_TASK, URGYM_INST_GEOM>(M, A, s);
+}

@@ -83,15 +83,12 @@ template <int TASK> __device__ __forceinline__ void store_dyn(const StateView &s
 
 struct StepArgs {
     StateView st;
-    int64_t n, offset;
-    uint2 key;
-    uint32_t event;
-    int autoreset;
+    int64_t n;
     const float *actions;
     float *obs, *ach, *des, *rew;
     uint8_t *term, *trunc, *succ;
-    float *tobs, *tach;
     unsigned long long *stats;
+    uint32_t *event;            // device-resident reset-event counter (bumped once per step launch)
     const float4 *hull;
 };
 
@@ -105,198 +102,265 @@ template <int GEOM> __device__ __forceinline__ const float4 *stage_hull(const fl
     return s;
 }
 template <int TASK, int GEOM> constexpr size_t step_smem_bytes() {
-    return (size_t)URGYM_BLOCK * (Traits<TASK>::OBS + 6) * sizeof(float) + URGYM_BLOCK * sizeof(int) +
+    return (size_t)URGYM_BLOCK * (Traits<TASK>::OBS + 6) * sizeof(float) +
            (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
 
 // ------------------------------------------------------------------------------------------------ step
+// One env per thread; every warp owns a private 32-row tile of the action and observation arrays in shared memory,
+// so apart from the hull staging (hull mode) and the block's statistics there is no block-wide synchronisation.
+// Finished envs are NOT reset here: the step only raises their terminated / truncated flags, and the auto-reset
+// kernel that follows in the stream handles them in dense form.
 template <int TASK, int GEOM>
 __global__ void __launch_bounds__(URGYM_BLOCK) urgym_step_kernel(const __grid_constant__ ModelConst c_model, const StepArgs A) {
     typedef Traits<TASK> TT;
-    constexpr int D = TT::OBS, G = TT::GOAL, B = URGYM_BLOCK;
+    constexpr int D = TT::OBS, G = TT::GOAL, B = URGYM_BLOCK, W = 32;
     extern __shared__ float4 smem4[];
-    float *s_obs = reinterpret_cast<float *>(smem4);          // [B][D]
-    float *s_act = s_obs + B * D;                             // [B][6]
-    int *s_list = reinterpret_cast<int *>(s_act + B * 6);     // [B] rows that finished this step
-    float4 *s_hull = reinterpret_cast<float4 *>(s_list + B);
-    __shared__ int s_ndone;
+    float *s_obs_all = reinterpret_cast<float *>(smem4);      // [B][D]
+    float *s_act_all = s_obs_all + B * D;                     // [B][6]
+    float4 *s_hull = reinterpret_cast<float4 *>(s_act_all + B * 6);
     __shared__ unsigned long long s_stats[URGYM_STATS_COUNT];
 
-    const int tid = threadIdx.x;
-    const int64_t base = (int64_t)blockIdx.x * B;
-    const int rows = (A.n - base) < B ? (int)(A.n - base) : B;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < URGYM_STATS_COUNT) s_stats[tid] = 0ull;
-    if (tid == 0) s_ndone = 0;
-
-    // action tile: 16-byte vectorised, coalesced
-    const float *gact = A.actions + base * 6;
-    if (rows == B && aligned16(gact)) {
-        const float4 *g4 = reinterpret_cast<const float4 *>(gact);
-        float4 *s4 = reinterpret_cast<float4 *>(s_act);
-        for (int k = tid; k < B * 6 / 4; k += B) s4[k] = __ldcs(g4 + k);
-    } else {
-        for (int k = tid; k < rows * 6; k += B) s_act[k] = gact[k];
-    }
+    if (blockIdx.x == 0 && tid == 0) *A.event += 1u;          // this launch is reset event number *A.event
     const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
     __syncthreads();
 
-    const bool active = tid < rows;
-    const int64_t i = base + tid;
-    float *row = s_obs + tid * D;
-    bool will_reset = false;
-    if (active) {
+    const int64_t wbase = (int64_t)blockIdx.x * B + warp * W;                 // first env of this warp
+    const int rows = (A.n - wbase) < W ? (int)max((long long)(A.n - wbase), 0ll) : W;
+    float *s_obs = s_obs_all + warp * W * D, *s_act = s_act_all + warp * W * 6;
+
+    // action tile: 16-byte vectorised, coalesced
+    if (rows > 0) {
+        const float *gact = A.actions + wbase * 6;
+        if (rows == W && aligned16(gact)) {
+            const float4 *g4 = reinterpret_cast<const float4 *>(gact);
+            float4 *s4 = reinterpret_cast<float4 *>(s_act);
+            for (int k = lane; k < W * 6 / 4; k += W) s4[k] = __ldcs(g4 + k);
+        } else {
+            for (int k = lane; k < rows * 6; k += W) s_act[k] = gact[k];
+        }
+    }
+    __syncwarp();
+
+    const int64_t i = wbase + lane;
+    if (lane < rows) {
         EnvState s;
         StepOut o;
         float vel[6];
         load_dyn<TASK>(A.st, i, s);
         load_E<TASK>(A.st, i, s.E);
-        const int len_before = s.elapsed;
-        env_step<TASK, GEOM>(c_model, s, s_act + tid * 6, hv, row, o, vel);
+        env_step<TASK, GEOM>(c_model, s, s_act + lane * 6, hv, s_obs + lane * D, o, vel);
+        store_dyn<TASK>(A.st, i, s);
         A.rew[i] = o.reward;
         A.term[i] = o.terminated ? 1 : 0;
         A.trunc[i] = o.truncated ? 1 : 0;
         A.succ[i] = o.success ? 1 : 0;
-        const bool done = o.terminated || o.truncated;
-        if (done) {
+        if (o.terminated || o.truncated) {
             atomicAdd(&s_stats[0], 1ull);
             atomicAdd(&s_stats[1], (unsigned long long)__float2ll_rn(s.ep_ret * URGYM_RETURN_SCALE));
-            atomicAdd(&s_stats[2], (unsigned long long)(len_before + 1));
+            atomicAdd(&s_stats[2], (unsigned long long)s.elapsed);
             if (o.success) atomicAdd(&s_stats[3], 1ull);
             if (o.collision) atomicAdd(&s_stats[4], 1ull);
             if (o.truncated && !o.terminated) atomicAdd(&s_stats[5], 1ull);
         }
-        will_reset = done && A.autoreset;
-        if (!will_reset) store_dyn<TASK>(A.st, i, s);
     }
-    // compaction of the finished rows: warp ballot, one shared-memory atomic per warp
-    {
-        const unsigned m = __ballot_sync(0xffffffffu, will_reset);
-        if (m) {
-            const int lane = tid & 31;
-            int pos = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) pos = atomicAdd(&s_ndone, __popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, leader);
-            if (will_reset) s_list[pos + __popc(m & ((1u << lane) - 1u))] = tid;
-        }
-    }
-    __syncthreads();
-    const int nd = s_ndone;
-    if (nd > 0) {
-        // terminal observations (DummyVecEnv's info["terminal_observation"]): whole rows, coalesced per row
-        if (A.tobs) {
-            for (int k = tid; k < nd * D; k += B) {
-                const int r = s_list[k / D], c = k % D;
-                A.tobs[(base + r) * D + c] = s_obs[r * D + c];
-            }
-        }
-        if (A.tach) {
-            for (int k = tid; k < nd * G; k += B) {
-                const int r = s_list[k / G], c = k % G;
-                A.tach[(base + r) * G + c] = s_obs[r * D + c];
-            }
-        }
-        __syncthreads();
-        // auto-reset: thread t takes the t-th finished row, so the rejection loops run in dense warps
-        if (tid < nd) {
-            const int r = s_list[tid];
-            const int64_t gi = base + r;
-            const uint64_t genv = (uint64_t)(A.offset + gi);
-            EnvState ns;
-            ResetStream rs;
-            rs.key = A.key; rs.episode = A.event; rs.env_lo = (uint32_t)genv; rs.env_hi = (uint32_t)(genv >> 32);
-            rs.bpi = TT::BPI; rs.iter = 0;
-            float *nrow = s_obs + r * D;
-            if (TT::DYN) {      // the previous episode's last velocity stays visible until the next step (quirk Q4)
-                A.st.va[gi] = make_float4(nrow[24], nrow[25], nrow[26], nrow[27]);
-                A.st.vb[gi] = make_float2(nrow[28], nrow[29]);
-            }
-            const int iters = env_reset<TASK, GEOM>(c_model, ns, rs, hv, nrow);
-            store_dyn<TASK>(A.st, gi, ns);
-            store_E<TASK>(A.st, gi, ns.E);
-            atomicAdd(&s_stats[7], (unsigned long long)iters);
-        }
-        __syncthreads();
-    }
+    __syncwarp();
     // observation tile -> global, 16-byte vectorised
-    float *gobs = A.obs + base * D;
-    if (rows == B && aligned16(gobs)) {
-        float4 *g4 = reinterpret_cast<float4 *>(gobs);
-        const float4 *s4 = reinterpret_cast<const float4 *>(s_obs);
-        for (int k = tid; k < B * D / 4; k += B) __stcs(g4 + k, s4[k]);
-    } else {
-        for (int k = tid; k < rows * D; k += B) gobs[k] = s_obs[k];
+    if (rows > 0) {
+        float *gobs = A.obs + wbase * D;
+        if (rows == W && aligned16(gobs)) {
+            float4 *g4 = reinterpret_cast<float4 *>(gobs);
+            const float4 *s4 = reinterpret_cast<const float4 *>(s_obs);
+            for (int k = lane; k < W * D / 4; k += W) __stcs(g4 + k, s4[k]);
+        } else {
+            for (int k = lane; k < rows * D; k += W) gobs[k] = s_obs[k];
+        }
+        if (A.ach) {        // achieved_goal = ee position (+ Euler) = first G observation columns
+            float *g = A.ach + wbase * G;
+            for (int k = lane; k < rows * G; k += W) g[k] = s_obs[(k / G) * D + (k % G)];
+        }
+        if (A.des) {        // desired_goal = goal = observation columns 12..12+G
+            float *g = A.des + wbase * G;
+            for (int k = lane; k < rows * G; k += W) g[k] = s_obs[(k / G) * D + 12 + (k % G)];
+        }
+        if (lane == 0) atomicAdd(&s_stats[6], (unsigned long long)rows);
     }
-    if (A.ach) {        // achieved_goal = ee position (+ Euler) = first G observation columns
-        float *g = A.ach + base * G;
-        for (int k = tid; k < rows * G; k += B) g[k] = s_obs[(k / G) * D + (k % G)];
-    }
-    if (A.des) {        // desired_goal = goal = observation columns 12..12+G
-        float *g = A.des + base * G;
-        for (int k = tid; k < rows * G; k += B) g[k] = s_obs[(k / G) * D + 12 + (k % G)];
-    }
-    if (tid == 0) atomicAdd(&s_stats[6], (unsigned long long)rows);
     __syncthreads();
     if (tid < URGYM_STATS_COUNT && s_stats[tid] != 0ull)
         atomicAdd(&A.stats[(blockIdx.x % URGYM_STAT_SLOTS) * URGYM_STATS_COUNT + tid], s_stats[tid]);
 }
 
-// ------------------------------------------------------------------------------------------------ reset / observe / refresh
+// ------------------------------------------------------------------------------------------------ reset / auto-reset
 struct AuxArgs {
     StateView st;
     int64_t n, offset;
     uint2 key;
-    uint32_t event;
-    const uint8_t *mask;
+    const uint8_t *mask, *mask2;    // reset env i when (mask ? mask[i] : 1) | (mask2 ? mask2[i] : 0); both NULL: all envs
+    int autoreset;                  // 1: called after a step (keep the terminal observation, velocity from the obs row)
     float *obs, *ach, *des;
+    float *tobs, *tach;             // auto-reset: terminal observation / achieved goal rows of the finished envs
     uint8_t *collision;
     unsigned long long *stats;
+    const uint32_t *event;
     const float4 *hull;
 };
+
+#define URGYM_RESET_GROUP 128       /* envs scanned by one warp of the reset kernel */
+
+// RobotTaskEnv.reset for the envs selected by the masks (core.py:263-273), in dense form: every warp scans 128
+// consecutive envs, compacts the selected ones with warp ballots, and resets them 32 at a time, one env per lane.
+// ReachDyn's rejection loop accepts only ~17.5 % of its draws on the cheap start-end distance rule, so that part
+// of the search runs 4 iterations per env in parallel (4-lane groups, 8 envs per pass) before the lane-per-env
+// phase evaluates the surviving iteration completely.
+template <int TASK, int GEOM>
+__global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
+    typedef Traits<TASK> TT;
+    constexpr int D = TT::OBS, G = TT::GOAL, W = 32, NW = URGYM_BLOCK / 32;
+    extern __shared__ float4 smem4[];
+    float *s_rows_all = reinterpret_cast<float *>(smem4);                    // [NW][32][D] new observation rows
+    int *s_list_all = reinterpret_cast<int *>(s_rows_all + NW * W * D);      // [NW][128] selected envs (local index)
+    int *s_k_all = s_list_all + NW * URGYM_RESET_GROUP;                      // [NW][128] first iteration to evaluate
+    float4 *s_hull = reinterpret_cast<float4 *>(s_k_all + NW * URGYM_RESET_GROUP);
+    const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
+    if (GEOM == GEOM_HULL) __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *s_rows = s_rows_all + warp * W * D;
+    int *s_list = s_list_all + warp * URGYM_RESET_GROUP, *s_k = s_k_all + warp * URGYM_RESET_GROUP;
+    const int64_t gbase = ((int64_t)blockIdx.x * NW + warp) * URGYM_RESET_GROUP;
+    if (gbase >= A.n) return;
+    const uint32_t event = *A.event;
+
+    // 1. compaction of the selected envs of this group
+    int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < URGYM_RESET_GROUP / W; c++) {
+        const int64_t i = gbase + c * W + lane;
+        bool sel = false;
+        if (i < A.n) {
+            sel = (A.mask == nullptr && A.mask2 == nullptr);
+            if (A.mask) sel = sel || A.mask[i] != 0;
+            if (A.mask2) sel = sel || A.mask2[i] != 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, sel);
+        if (sel) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = c * W + lane;
+        cnt += __popc(m);
+    }
+    if (cnt == 0) return;
+    __syncwarp();
+
+    // 2. auto-reset: the rows still hold the final observation of the finished episodes -> terminal observation
+    if (A.autoreset && (A.tobs || A.tach)) {
+        for (int j = 0; j < cnt; j++) {
+            const int64_t i = gbase + s_list[j];
+            for (int c = lane; c < D; c += W) {
+                const float v = A.obs[i * D + c];
+                if (A.tobs) A.tobs[i * D + c] = v;
+                if (A.tach && c < G) A.tach[i * G + c] = v;
+            }
+        }
+    }
+
+    // 3. ReachDyn: first iteration that passes the start-end distance rule, 4 candidate iterations per env at a time
+    for (int j = lane; j < cnt; j += W) s_k[j] = 0;
+    __syncwarp();
+    if (TT::DYN) {
+        const int sub = lane & 3, grp = lane >> 2;
+        for (int j0 = 0; j0 < cnt; j0 += 8) {
+            const int j = j0 + grp;
+            const bool have = j < cnt;
+            ResetStream rs;
+            rs.key = A.key; rs.episode = event; rs.bpi = TT::BPI; rs.iter = 0; rs.env_lo = rs.env_hi = 0;
+            if (have) {
+                const uint64_t genv = (uint64_t)(A.offset + gbase + s_list[j]);
+                rs.env_lo = (uint32_t)genv; rs.env_hi = (uint32_t)(genv >> 32);
+            }
+            bool found = !have;
+            int kstar = 0;
+            for (int k0 = 0; k0 < URGYM_MAX_RESET_ITERS; k0 += 4) {
+                bool ok = false;
+                if (!found) { rs.iter = (uint32_t)(k0 + sub); ok = dyn_pair_far_enough(rs); }
+                const unsigned gm = (__ballot_sync(0xffffffffu, ok) >> (grp * 4)) & 0xFu;
+                if (!found && gm) { found = true; kstar = k0 + __ffs(gm) - 1; }
+                if (__all_sync(0xffffffffu, found)) break;
+            }
+            if (have && sub == 0) s_k[j] = found ? kstar : URGYM_MAX_RESET_ITERS - 1;
+        }
+        __syncwarp();
+    }
+
+    // 4. one env per lane: complete sample from iteration s_k on, neutral pose, link distances, first observation
+    unsigned long long iters_total = 0ull;
+    for (int j0 = 0; j0 < cnt; j0 += W) {
+        const int j = j0 + lane;
+        if (j < cnt) {
+            const int64_t i = gbase + s_list[j];
+            const uint64_t genv = (uint64_t)(A.offset + i);
+            float *row = s_rows + lane * D;
+            EnvState s;
+            if (TT::DYN) {      // ReachDyn.velocity survives the reset (quirk Q4): carry what the last episode left
+                float vel[6];
+                if (A.autoreset) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) vel[k] = A.obs[i * D + 24 + k];
+                } else {
+                    load_dyn<TASK>(A.st, i, s);
+                    load_E<TASK>(A.st, i, s.E);
+                    if (s.elapsed == 0) {
+                        float4 a = A.st.va[i]; float2 b = A.st.vb[i];
+                        vel[0] = a.x; vel[1] = a.y; vel[2] = a.z; vel[3] = a.w; vel[4] = b.x; vel[5] = b.y;
+                    } else {
+                        Quat qs; float3 axis; float angle; float tw[6];
+                        dyn_twist(&s.E[6], &s.E[12], tw, qs, axis, angle);
+#pragma unroll
+                        for (int k = 0; k < 6; k++) vel[k] = s.elapsed <= 25 ? tw[k] : 0.0f;
+                    }
+                }
+                A.st.va[i] = make_float4(vel[0], vel[1], vel[2], vel[3]);
+                A.st.vb[i] = make_float2(vel[4], vel[5]);
+#pragma unroll
+                for (int k = 0; k < 6; k++) row[24 + k] = vel[k];
+            }
+            ResetStream rs;
+            rs.key = A.key; rs.episode = event; rs.env_lo = (uint32_t)genv; rs.env_hi = (uint32_t)(genv >> 32);
+            rs.bpi = TT::BPI; rs.iter = 0;
+            iters_total += (unsigned long long)env_reset<TASK, GEOM>(c_model, s, rs, hv, row, s_k[j]);
+            store_dyn<TASK>(A.st, i, s);
+            store_E<TASK>(A.st, i, s.E);
+        }
+        __syncwarp();
+        // new rows -> global, one row at a time (rows of reset envs are scattered)
+        const int nrows = min(W, cnt - j0);
+        for (int r = 0; r < nrows; r++) {
+            const int64_t i = gbase + s_list[j0 + r];
+            const float *row = s_rows + r * D;
+            for (int c = lane; c < D; c += W) {
+                const float v = row[c];
+                if (A.obs) A.obs[i * D + c] = v;
+                if (A.ach && c < G) A.ach[i * G + c] = v;
+                if (A.des && c >= 12 && c < 12 + G) A.des[i * G + c - 12] = v;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) iters_total += __shfl_xor_sync(0xffffffffu, iters_total, o);
+    if (lane == 0) atomicAdd(&A.stats[(blockIdx.x % URGYM_STAT_SLOTS) * URGYM_STATS_COUNT + 7], iters_total);
+}
+template <int TASK, int GEOM> constexpr size_t reset_smem_bytes() {
+    return (size_t)URGYM_BLOCK * Traits<TASK>::OBS * sizeof(float) + 2 * (URGYM_BLOCK / 32) * URGYM_RESET_GROUP * sizeof(int) +
+           (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
+}
+
+static __global__ void urgym_bump_kernel(uint32_t *event) { *event += 1u; }
 
 template <int TASK> __device__ __forceinline__ void write_rows(const AuxArgs &A, int64_t i, const float *row) {
     constexpr int D = Traits<TASK>::OBS, G = Traits<TASK>::GOAL;
     if (A.obs) for (int k = 0; k < D; k++) A.obs[i * D + k] = row[k];
     if (A.ach) for (int k = 0; k < G; k++) A.ach[i * G + k] = row[k];
     if (A.des) for (int k = 0; k < G; k++) A.des[i * G + k] = row[12 + k];
-}
-
-template <int TASK, int GEOM>
-__global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
-    typedef Traits<TASK> TT;
-    extern __shared__ float4 smem4[];
-    const float4 *hv = stage_hull<GEOM>(A.hull, smem4);
-    if (GEOM == GEOM_HULL) __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * URGYM_BLOCK + threadIdx.x;
-    if (i >= A.n || (A.mask && !A.mask[i])) return;
-    float row[TT::OBS];
-    EnvState s;
-    if (TT::DYN) {
-        // ReachDyn.velocity survives the reset (quirk Q4): carry the value the previous episode ended with
-        load_dyn<TASK>(A.st, i, s);
-        load_E<TASK>(A.st, i, s.E);
-        float vel[6];
-        if (s.elapsed == 0) {
-            float4 a = A.st.va[i]; float2 b = A.st.vb[i];
-            vel[0] = a.x; vel[1] = a.y; vel[2] = a.z; vel[3] = a.w; vel[4] = b.x; vel[5] = b.y;
-        } else {
-            Quat qs; float3 axis; float angle; float tw[6];
-            dyn_twist(&s.E[6], &s.E[12], tw, qs, axis, angle);
-            for (int k = 0; k < 6; k++) vel[k] = s.elapsed <= 25 ? tw[k] : 0.0f;
-        }
-        A.st.va[i] = make_float4(vel[0], vel[1], vel[2], vel[3]);
-        A.st.vb[i] = make_float2(vel[4], vel[5]);
-        for (int k = 0; k < 6; k++) row[24 + k] = vel[k];
-    }
-    const uint64_t genv = (uint64_t)(A.offset + i);
-    ResetStream rs;
-    rs.key = A.key; rs.episode = A.event; rs.env_lo = (uint32_t)genv; rs.env_hi = (uint32_t)(genv >> 32);
-    rs.bpi = TT::BPI; rs.iter = 0;
-    const int iters = env_reset<TASK, GEOM>(c_model, s, rs, hv, row);
-    store_dyn<TASK>(A.st, i, s);
-    store_E<TASK>(A.st, i, s.E);
-    write_rows<TASK>(A, i, row);
-    atomicAdd(&A.stats[(blockIdx.x % URGYM_STAT_SLOTS) * URGYM_STATS_COUNT + 7], (unsigned long long)iters);
 }
 
 template <int TASK>
@@ -336,33 +400,30 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_refresh_kernel(const __grid
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + URGYM_BLOCK - 1) / URGYM_BLOCK); }
 
 template <int TASK, int GEOM> cudaError_t launch_step(const ModelConst &M, const StepArgs &A, cudaStream_t s) {
-    const size_t smem = step_smem_bytes<TASK, GEOM>();
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(urgym_step_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    urgym_step_kernel<TASK, GEOM><<<grid_for(A.n), URGYM_BLOCK, smem, s>>>(M, A);
+    urgym_step_kernel<TASK, GEOM><<<grid_for(A.n), URGYM_BLOCK, step_smem_bytes<TASK, GEOM>(), s>>>(M, A);
     return cudaGetLastError();
 }
 template <int TASK, int GEOM> cudaError_t launch_reset(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
-    const size_t smem = GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(urgym_reset_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    urgym_reset_kernel<TASK, GEOM><<<grid_for(A.n), URGYM_BLOCK, smem, s>>>(M, A);
+    const int64_t per_block = (int64_t)(URGYM_BLOCK / 32) * URGYM_RESET_GROUP;
+    urgym_reset_kernel<TASK, GEOM><<<(unsigned)((A.n + per_block - 1) / per_block), URGYM_BLOCK, reset_smem_bytes<TASK, GEOM>(), s>>>(M, A);
     return cudaGetLastError();
 }
 template <int TASK, int GEOM> cudaError_t launch_refresh(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     const size_t smem = GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(urgym_refresh_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
     urgym_refresh_kernel<TASK, GEOM><<<grid_for(A.n), URGYM_BLOCK, smem, s>>>(M, A);
     return cudaGetLastError();
 }
-
+// opt the (task, geometry) kernels in to the dynamic shared memory they need (once, at urgym_create: not legal
+// while a stream is being captured into a CUDA graph)
+template <int TASK, int GEOM> cudaError_t prepare_kernels(const ModelConst &, const AuxArgs &, cudaStream_t) {
+    cudaError_t e = cudaFuncSetAttribute(urgym_step_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes<TASK, GEOM>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(urgym_reset_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reset_smem_bytes<TASK, GEOM>());
+    if (e != cudaSuccess) return e;
+    const size_t smem = GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
+    if (smem) e = cudaFuncSetAttribute(urgym_refresh_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e;
+}
 
 template <int TASK> cudaError_t launch_observe(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     urgym_observe_kernel<TASK><<<grid_for(A.n), URGYM_BLOCK, 0, s>>>(M, A);
@@ -375,6 +436,7 @@ typedef cudaError_t (*aux_launcher_t)(const ModelConst &, const AuxArgs &, cudaS
 #define URGYM_DECLARE_INST(T, G)                                                           \
     cudaError_t urgym_inst_step_##T##_##G(const ModelConst &, const StepArgs &, cudaStream_t);   \
     cudaError_t urgym_inst_reset_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);   \
-    cudaError_t urgym_inst_refresh_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);
+    cudaError_t urgym_inst_refresh_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);      \
+    cudaError_t urgym_inst_prepare_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);
 URGYM_DECLARE_INST(0, 0) URGYM_DECLARE_INST(1, 0) URGYM_DECLARE_INST(2, 0) URGYM_DECLARE_INST(3, 0)
 URGYM_DECLARE_INST(0, 1) URGYM_DECLARE_INST(1, 1) URGYM_DECLARE_INST(2, 1) URGYM_DECLARE_INST(3, 1)

@@ -56,6 +56,10 @@ class UR5VecEnv:
         # off by default because they are views of the observation buffers here
         self.achieved = torch.zeros((n, G), dtype=torch.float32, **kw) if goal_buffers else None
         self.terminal_achieved = torch.zeros((n, G), dtype=torch.float32, **kw) if goal_buffers else None
+        self._step_ptrs = [_ptr(self.obs), _ptr(self.achieved), None, _ptr(self.reward), _ptr(self.terminated),
+                           _ptr(self.truncated), _ptr(self.is_success), _ptr(self.terminal_obs), _ptr(self.terminal_achieved)]
+        self._obs = self._obs_dict(self.obs)
+        self._info = {"is_success": self.is_success, "terminal_observation": self.terminal_obs}
 
     # ---- plumbing
     def _stream(self):
@@ -81,26 +85,41 @@ class UR5VecEnv:
         """reset all envs (mask None) or those with a non-zero mask byte; returns the observation dict"""
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        with torch.cuda.device(self.device):
-            nat.check(self.h, self.L.urgym_reset(self.h, _ptr(mask), _ptr(self.obs), None, None, self._stream()))
-        return self._obs_dict(self.obs)
+        nat.check(self.h, self.L.urgym_reset(self.h, _ptr(mask), _ptr(self.obs), _ptr(self.achieved), None, self._stream()))
+        return self._obs
 
     def step(self, actions: torch.Tensor):
         """actions float32 [N,6] on the device.  Returns (obs dict, reward, terminated, truncated, info); for envs that
         finished, obs is the first observation of the next episode and info["terminal_observation"] rows hold the last
-        one (DummyVecEnv semantics)."""
+        one (DummyVecEnv semantics; `time_limit_truncated()` gives its "TimeLimit.truncated").  Two kernel launches
+        on the current torch stream (step, then the dense auto-reset of the finished envs), no synchronisation."""
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
         if actions.shape != (self.num_envs, 6):
             raise ValueError(f"actions must have shape ({self.num_envs}, 6)")
-        with torch.cuda.device(self.device):
-            nat.check(self.h, self.L.urgym_step(self.h, _ptr(actions), _ptr(self.obs), _ptr(self.achieved), None,
-                                                _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated),
-                                                _ptr(self.is_success), _ptr(self.terminal_obs),
-                                                _ptr(self.terminal_achieved), self._stream()))
-        info = {"is_success": self.is_success, "terminal_observation": self.terminal_obs,
-                "TimeLimit.truncated": self.truncated & (1 - self.terminated)}
-        return self._obs_dict(self.obs), self.reward, self.terminated, self.truncated, info
+        rc = self.L.urgym_step(self.h, actions.data_ptr(), *self._step_ptrs,
+                               torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            nat.check(self.h, rc)
+        return self._obs, self.reward, self.terminated, self.truncated, self._info
+
+    def time_limit_truncated(self) -> torch.Tensor:
+        """DummyVecEnv's info["TimeLimit.truncated"]: truncated and not terminated"""
+        return self.truncated & (1 - self.terminated)
+
+    def capture_steps(self, action_buffers) -> "torch.cuda.CUDAGraph":
+        """Capture one step per tensor of `action_buffers` (persistent device tensors the caller refills between
+        replays) into a CUDA graph; graph.replay() then advances len(action_buffers) env steps with one launch from the
+        host.  The reset-event counter lives on the device, so replays draw fresh episodes."""
+        for a in action_buffers:
+            if a.device != self.device or a.dtype != torch.float32 or not a.is_contiguous() or a.shape != (self.num_envs, 6):
+                raise ValueError("capture_steps needs contiguous float32 [N,6] tensors on the simulator's device")
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for a in action_buffers:
+                self.step(a)
+        return graph
 
     def reseed(self, seed: int) -> None:
         """re-key the counter-based reset stream (RobotTaskEnv.reset(seed=...), core.py:263-267)"""
