@@ -51,7 +51,8 @@ static void step_t(int64_t n, HcState S, const float *act, float *obs, float *re
     for (int64_t i = 0; i < n; i++) {
         EnvState s; StepOut o; float v[6] = {0, 0, 0, 0, 0, 0};
         get(S, i, s);
-        env_step<TASK, GEOM>(g_M, s, act + i * 6, g_hull.data(), obs + i * D, o, v);
+        float scratch[URGYM_SCRATCH_FLOATS];
+        env_step<TASK, GEOM>(g_M, s, act + i * 6, g_hull.data(), obs + i * D, o, v, scratch, 1);
         put(S, i, s);
         rew[i] = o.reward;
         flags[i * 4] = o.terminated; flags[i * 4 + 1] = o.truncated; flags[i * 4 + 2] = o.success; flags[i * 4 + 3] = o.collision;
@@ -76,7 +77,8 @@ static void refresh_t(int64_t n, HcState S, uint8_t *coll) {
     for (int64_t i = 0; i < n; i++) {
         EnvState s;
         get(S, i, s);
-        coll[i] = env_refresh<TASK, GEOM>(g_M, s, g_hull.data());
+        float scratch[URGYM_SCRATCH_FLOATS];
+        coll[i] = env_refresh<TASK, GEOM>(g_M, s, g_hull.data(), scratch, 1);
         put(S, i, s);
     }
 }
@@ -136,7 +138,7 @@ void hc_ee_pose(int64_t n, const float *q, float *ee) {
     for (int64_t i = 0; i < n; i++) {
         ObstW O; O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
         float du[5];
-        robot_pass<TASK_ORI, GEOM_CAPSULE>(g_M, q + i * 6, O, nullptr, false, ee + i * 6, du[0], du[1], du[2], du[3], du[4]);
+        robot_pass<TASK_ORI, GEOM_CAPSULE>(g_M, q + i * 6, q + i * 6, O, nullptr, false, ee + i * 6, du, nullptr, 1);
     }
 }
 void hc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {

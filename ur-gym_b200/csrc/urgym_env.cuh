@@ -100,7 +100,7 @@ URGYM_HD void dyn_twist(const float *start, const float *end, float *vel, Quat &
     float w = clampf(d.w, -1.0f, 1.0f);
     float s2 = 1.0f - d.w * d.w;
     float vn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);      // = sqrt(1 - w^2) for a unit quaternion, better conditioned
-    angle = 2.0f * atan2_ool(vn, w);                             // = 2 acos(w)
+    angle = 2.0f * atan2_fast(vn, w);                             // = 2 acos(w)
     if (s2 < 10.0f * 1.1920929e-7f || vn == 0.0f) axis = f3(1.0f, 0.0f, 0.0f);
     else axis = (1.0f / vn) * f3(d.x, d.y, d.z);
     vel[0] = (end[0] - start[0]) * 0.5f; vel[1] = (end[1] - start[1]) * 0.5f; vel[2] = (end[2] - start[2]) * 0.5f;
@@ -273,7 +273,7 @@ URGYM_HD float target_obstacle_dist(const ModelConst &M, const float *goal, cons
 // ee[6] = EE position + PyBullet Euler triple (UR5.py:320-325,334-340); d0..d4 = link 2..6 <-> obstacle distances.
 // q is read through `qrow` (memory, e.g. the joint columns of the observation row) so the loop can stay rolled.
 template <int TASK, int GEOM>
-URGYM_HD bool robot_pass(const ModelConst &M, const float *qrow, const ObstW &O, const float4 *hv, bool collide,
+URGYM_HD bool robot_pass_rolled(const ModelConst &M, const float *qrow, const ObstW &O, const float4 *hv, bool collide,
                          float *ee, float &d0, float &d1, float &d2, float &d3, float &d4) {
     Pose T;
     pose_identity(T);
@@ -302,6 +302,85 @@ URGYM_HD bool robot_pass(const ModelConst &M, const float *qrow, const ObstW &O,
     float3 e = euler_from_mat(T.R);
     ee[0] = T.p.x; ee[1] = T.p.y; ee[2] = T.p.z; ee[3] = e.x; ee[4] = e.y; ee[5] = e.z;
     return hit;
+}
+
+// The capsule-geometry version of the same pass.  Phase 1, fully unrolled (the per-joint constants become immediate
+// constant-bank operands): FK and the world capsule segment of every link, parked in a per-thread scratch column
+// (`cap[k * cs]`: shared memory on the device, conflict-free with cs = 32).  Phase 2, rolled loops over links and
+// link pairs, so each distance routine exists once in the instruction stream.
+// scratch layout: 36 floats capsule endpoints (link 1..6: a.xyz b.xyz), 5 floats link-obstacle distances.
+#define URGYM_SCRATCH_FLOATS 41
+template <int TASK>
+URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const ObstW &O, bool collide, float *ee,
+                                 float *dist, float *cap, int cs) {
+    Pose T;
+    pose_identity(T);
+#pragma unroll
+    for (int l = 1; l < 7; l++) {
+        fk_advance(M, T, l - 1, q[l - 1]);
+        if (collide) {
+            float3 a = T.p + rot(T.R, f3(M.cap_p0[l][0], M.cap_p0[l][1], M.cap_p0[l][2]));
+            float3 b = T.p + rot(T.R, f3(M.cap_p1[l][0], M.cap_p1[l][1], M.cap_p1[l][2]));
+            float *c = cap + (l - 1) * 6 * cs;
+            c[0] = a.x; c[cs] = a.y; c[2 * cs] = a.z; c[3 * cs] = b.x; c[4 * cs] = b.y; c[5 * cs] = b.z;
+        }
+    }
+    float3 e = euler_from_mat(T.R);
+    ee[0] = T.p.x; ee[1] = T.p.y; ee[2] = T.p.z; ee[3] = e.x; ee[4] = e.y; ee[5] = e.z;
+    if (!collide) return false;
+    bool hit = false;
+    // links 2..6 vs obstacle (distances kept: they are get_link_distances' values), table and track
+    const float3 oa = O.c - M.obst_cap_h * O.u, ob = O.c + M.obst_cap_h * O.u;
+#pragma unroll 1
+    for (int l = 2; l < 7; l++) {
+        const float *c = cap + (l - 1) * 6 * cs;
+        const float3 a = f3(c[0], c[cs], c[2 * cs]), b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
+        const float m = M.cap_m[l];
+        if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
+            float d = sqrtf(segseg_dist2_fast(a, b, oa, ob, M.cap_ia[l], M.obst_cap_ie)) - m - M.obst_cap_m;
+            hit = hit || (d <= URGYM_COLLISION_MARGIN);
+            cap[(36 + l - 2) * cs] = d;
+        }
+        // height broad phase: both boxes lie below z = box_top, most links stay well above it
+        if (fminf(a.z, b.z) - (URGYM_COLLISION_MARGIN + m + M.box_margin[0]) <= M.box_top) {
+#pragma unroll 1
+            for (int box = 0; box < 2; box++) {
+                float margin = M.box_margin[box];
+                float reach = URGYM_COLLISION_MARGIN + m + margin;
+                float3 bc = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
+                float3 bh = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
+                if (seg_box_lower2(a, b, bc, bh) <= reach * reach)
+                    hit = hit || (sqrtf(seg_box_dist2(a, b, bc, bh)) - m - margin <= URGYM_COLLISION_MARGIN);
+            }
+        }
+    }
+    // self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6)
+#pragma unroll 1
+    for (int p = 0; p < 9; p++) {
+        const int l1 = p < 4 ? 1 : (p < 7 ? 2 : 3);
+        const int l2 = p < 4 ? p + 3 : (p < 7 ? p : p - 2);
+        const float *c1 = cap + (l1 - 1) * 6 * cs, *c2 = cap + (l2 - 1) * 6 * cs;
+        const float3 a1 = f3(c1[0], c1[cs], c1[2 * cs]), b1 = f3(c1[3 * cs], c1[4 * cs], c1[5 * cs]);
+        const float3 a2 = f3(c2[0], c2[cs], c2[2 * cs]), b2 = f3(c2[3 * cs], c2[4 * cs], c2[5 * cs]);
+        const float reach = URGYM_COLLISION_MARGIN + M.cap_m[l1] + M.cap_m[l2];
+        const float3 dm = 0.5f * ((a1 + b1) - (a2 + b2));
+        const float far = reach + M.cap_hl[l1] + M.cap_hl[l2];
+        if (dot(dm, dm) <= far * far)       // sphere broad phase (exact bound)
+            hit = hit || (segseg_dist2_fast(a1, b1, a2, b2, M.cap_ia[l1], M.cap_ia[l2]) <= reach * reach);
+    }
+    if (Traits<TASK>::HAS_OBST) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) dist[k] = cap[(36 + k) * cs];
+    }
+    return hit;
+}
+
+// geometry dispatch.  qrow: joint angles in memory (rolled hull pass); q: the same in registers (capsule pass)
+template <int TASK, int GEOM>
+URGYM_HD bool robot_pass(const ModelConst &M, const float *q, const float *qrow, const ObstW &O, const float4 *hv,
+                         bool collide, float *ee, float *dist, float *scratch, int cs) {
+    if (GEOM == GEOM_CAPSULE) return robot_pass_capsule<TASK>(M, q, O, collide, ee, dist, scratch, cs);
+    return robot_pass_rolled<TASK, GEOM>(M, qrow, O, hv, collide, ee, dist[0], dist[1], dist[2], dist[3], dist[4]);
 }
 
 // task part of the observation   reach.py:189-190 (Ori), 307-308 (Obs), 454-458 (Sta), 653-657 (Dyn)
@@ -355,7 +434,7 @@ URGYM_HD bool goal_metrics(const float *ee, const float *E, float &d, float &ang
 // (OBS floats).  vel_out (Dyn, 6 floats): ReachDyn.velocity after this step.
 template <int TASK, int GEOM>
 URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const float4 *hv, float *row, StepOut &o,
-                       float *vel_out) {
+                       float *vel_out, float *scratch, int cs) {
     typedef Traits<TASK> TT;
     // 1. UR5Ori.set_action: clip, * pi, * 0.1 (float32 like the numpy expression), teleport      UR5.py:273-279,314-317
 #pragma unroll
@@ -383,7 +462,7 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
     float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int k = 0; k < 6; k++) row[6 + k] = s.q[k];
-    bool coll = robot_pass<TASK, GEOM>(M, row + 6, O, hv, true, ee, dist[0], dist[1], dist[2], dist[3], dist[4]);
+    bool coll = robot_pass<TASK, GEOM>(M, s.q, row + 6, O, hv, true, ee, dist, scratch, cs);
     // 4. observation: carries link_dist from BEFORE this step's reward (quirk Q1)               core.py:311
     write_obs_row<TASK>(row, ee, s.q, s.E, O, vel, s.ld);
     // 5. termination                                                                           core.py:313-315
@@ -449,14 +528,14 @@ URGYM_HD void env_observe(const ModelConst &M, const EnvState &s, const float *s
     float ee[6], du[5];
 #pragma unroll
     for (int k = 0; k < 6; k++) row[6 + k] = s.q[k];
-    robot_pass<TASK, GEOM_CAPSULE>(M, row + 6, O, nullptr, false, ee, du[0], du[1], du[2], du[3], du[4]);   // EE pose only
+    robot_pass<TASK, GEOM_CAPSULE>(M, s.q, row + 6, O, nullptr, false, ee, du, nullptr, 1);   // EE pose only
     write_obs_row<TASK>(row, ee, s.q, s.E, O, vel, s.ld);
 }
 
 // tail of set_goal_and_obstacle / reset: collision flag and link_dist = last_dist at the current state
 // reach.py:322-324,333-335,477-479,501-503,679-681,711-713
 template <int TASK, int GEOM>
-URGYM_HD bool env_refresh(const ModelConst &M, EnvState &s, const float4 *hv) {
+URGYM_HD bool env_refresh(const ModelConst &M, EnvState &s, const float4 *hv, float *scratch, int cs) {
     typedef Traits<TASK> TT;
     ObstW O;
     if (TT::DYN) {
@@ -469,7 +548,7 @@ URGYM_HD bool env_refresh(const ModelConst &M, EnvState &s, const float4 *hv) {
         O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
     }
     float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    bool coll = robot_pass<TASK, GEOM>(M, s.q, O, hv, true, ee, dist[0], dist[1], dist[2], dist[3], dist[4]);
+    bool coll = robot_pass<TASK, GEOM>(M, s.q, s.q, O, hv, true, ee, dist, scratch, cs);
     if (TT::HAS_OBST) {
 #pragma unroll
         for (int k = 0; k < 5; k++) s.ld[k] = dist[k];

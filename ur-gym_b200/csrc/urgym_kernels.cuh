@@ -102,7 +102,7 @@ template <int GEOM> __device__ __forceinline__ const float4 *stage_hull(const fl
     return s;
 }
 template <int TASK, int GEOM> constexpr size_t step_smem_bytes() {
-    return (size_t)URGYM_BLOCK * (Traits<TASK>::OBS + 6) * sizeof(float) +
+    return (size_t)URGYM_BLOCK * (Traits<TASK>::OBS + 6 + (GEOM == GEOM_CAPSULE ? URGYM_SCRATCH_FLOATS : 0)) * sizeof(float) +
            (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
 
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_step_kernel(const __grid_co
     extern __shared__ float4 smem4[];
     float *s_obs_all = reinterpret_cast<float *>(smem4);      // [B][D]
     float *s_act_all = s_obs_all + B * D;                     // [B][6]
-    float4 *s_hull = reinterpret_cast<float4 *>(s_act_all + B * 6);
+    float *s_scr_all = s_act_all + B * 6;                     // [warps][URGYM_SCRATCH_FLOATS][32] (capsule geometry)
+    float4 *s_hull = reinterpret_cast<float4 *>(s_scr_all + (GEOM == GEOM_CAPSULE ? B * URGYM_SCRATCH_FLOATS : 0));
     __shared__ unsigned long long s_stats[URGYM_STATS_COUNT];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -151,7 +152,8 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_step_kernel(const __grid_co
         float vel[6];
         load_dyn<TASK>(A.st, i, s);
         load_E<TASK>(A.st, i, s.E);
-        env_step<TASK, GEOM>(c_model, s, s_act + lane * 6, hv, s_obs + lane * D, o, vel);
+        env_step<TASK, GEOM>(c_model, s, s_act + lane * 6, hv, s_obs + lane * D, o, vel,
+                             s_scr_all + warp * W * URGYM_SCRATCH_FLOATS + lane, W);
         store_dyn<TASK>(A.st, i, s);
         A.rew[i] = o.reward;
         A.term[i] = o.terminated ? 1 : 0;
@@ -177,13 +179,18 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_step_kernel(const __grid_co
         } else {
             for (int k = lane; k < rows * D; k += W) gobs[k] = s_obs[k];
         }
-        if (A.ach) {        // achieved_goal = ee position (+ Euler) = first G observation columns
-            float *g = A.ach + wbase * G;
-            for (int k = lane; k < rows * G; k += W) g[k] = s_obs[(k / G) * D + (k % G)];
-        }
-        if (A.des) {        // desired_goal = goal = observation columns 12..12+G
-            float *g = A.des + wbase * G;
-            for (int k = lane; k < rows * G; k += W) g[k] = s_obs[(k / G) * D + 12 + (k % G)];
+        if (lane < rows) {  // achieved_goal = first G observation columns, desired_goal = columns 12..12+G of the own row
+            const float *row = s_obs + lane * D;
+            if (A.ach) {
+                float *g = A.ach + (wbase + lane) * G;
+#pragma unroll
+                for (int k = 0; k < G; k++) g[k] = row[k];
+            }
+            if (A.des) {
+                float *g = A.des + (wbase + lane) * G;
+#pragma unroll
+                for (int k = 0; k < G; k++) g[k] = row[12 + k];
+            }
         }
         if (lane == 0) atomicAdd(&s_stats[6], (unsigned long long)rows);
     }
@@ -391,7 +398,8 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_refresh_kernel(const __grid
     EnvState s;
     load_dyn<TASK>(A.st, i, s);
     load_E<TASK>(A.st, i, s.E);
-    const bool coll = env_refresh<TASK, GEOM>(c_model, s, hv);
+    float scratch[URGYM_SCRATCH_FLOATS];
+    const bool coll = env_refresh<TASK, GEOM>(c_model, s, hv, scratch, 1);
     store_dyn<TASK>(A.st, i, s);
     if (A.collision) A.collision[i] = coll ? 1 : 0;
 }

@@ -45,6 +45,7 @@ static void build_model_const(ModelConst &M) {
         double hl = 0.0;
         for (int k = 0; k < 3; k++) hl += (UR5E_CAPSULE_P1[3 * l + k] - UR5E_CAPSULE_P0[3 * l + k]) * (UR5E_CAPSULE_P1[3 * l + k] - UR5E_CAPSULE_P0[3 * l + k]);
         M.cap_hl[l] = (float)(0.5 * sqrt(hl) + 1e-5);
+        M.cap_ia[l] = (float)(1.0 / hl);
     }
     for (int l = 0; l < 8; l++) M.hull_off[l] = UR5E_HULL_OFFSET[l];
     M.hull_margin = (float)hull_margin;
@@ -65,6 +66,8 @@ static void build_model_const(ModelConst &M) {
     // capsule mode: smallest bounding capsule of the cylinder (segment half length = half height, radius = radius);
     // target: the Obs sphere itself, the bounding sphere of the Sta/Dyn cube
     M.obst_cap_h = 0.2f; M.obst_cap_m = 0.05f;
+    M.obst_cap_ie = (float)(1.0 / (0.4 * 0.4));
+    M.box_top = (float)fmax(tc[2] + th[2] - pm, kc[2] + kh[2] - pm);
     M.tgt_cap_m[0] = 0.0f; M.tgt_cap_m[1] = 0.02f;
     M.tgt_cap_m[2] = M.tgt_cap_m[3] = (float)(0.025 * 1.7320508075688772);
     // reset pose                                                   UR5.py:262
