@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liburgym_b200.so")
+LIB_PATH = os.environ.get("URGYM_B200_LIB") or os.path.join(_HERE, "liburgym_b200.so")   # override: A/B builds while tuning
 
 TASK_IDS = {"UR5OriReach-v1": 0, "UR5ObsReach-v1": 1, "UR5StaReach-v1": 2, "UR5DynReach-v1": 3}
 GEOM_HULL, GEOM_CAPSULE = 0, 1

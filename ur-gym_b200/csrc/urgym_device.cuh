@@ -21,6 +21,13 @@
 // Out-of-line helpers: the libdevice bodies of sincosf / atan2f (range reduction, slow paths) and the Philox rounds
 // are big; one shared copy each keeps the step kernel's instruction footprint inside the instruction cache (the
 // first profile of the fully inlined kernel -- 13 k SASS instructions -- stalled on instruction fetch).
+// warp-level barrier inside the per-env functions (the capsule scratch overlays the warp's I/O tile); nothing to do
+// in the single-threaded host instantiation
+#ifdef __CUDA_ARCH__
+#define URGYM_WARP_SYNC() __syncwarp()
+#else
+#define URGYM_WARP_SYNC() ((void)0)
+#endif
 #if defined(__CUDACC__)
 #define URGYM_OOL __host__ __device__ __noinline__
 #else
@@ -291,13 +298,13 @@ URGYM_HD void fk_link(const ModelConst &M, const float *q, int link, Pose &T) {
 }
 
 // ------------------------------------------------------------------------------------------------ Philox4x32-10
+// Philox4x32-10 (Salmon et al., SC'11).  One 32x32->64 multiply gives both halves of each product (IMAD.WIDE).
 static URGYM_OOL uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll 1
+#pragma unroll
     for (int r = 0; r < 10; r++) {
         if (r) { k.x += 0x9E3779B9u; k.y += 0xBB67AE85u; }
-        uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c.x, p1 = (uint64_t)0xCD9E8D57u * c.z;
+        c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k.x, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ k.y, (uint32_t)p0);
     }
     return c;
 }

@@ -439,6 +439,7 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
     // 1. UR5Ori.set_action: clip, * pi, * 0.1 (float32 like the numpy expression), teleport      UR5.py:273-279,314-317
 #pragma unroll
     for (int j = 0; j < 6; j++) s.q[j] += (clampf(act[j], -1.0f, 1.0f) * URGYM_PI_F) * 0.1f;
+    URGYM_WARP_SYNC();      // `scratch` may overlay the action / observation tile: every lane has read its action
     // 2. task.set_velocity + sim.step: obstacle pose after this step                           core.py:305-309
     ObstW O;
     float vel[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -460,9 +461,12 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
     }
     // 3. FK and collision                                                                      core.py:310
     float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (GEOM != GEOM_CAPSULE) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) row[6 + k] = s.q[k];
+        for (int k = 0; k < 6; k++) row[6 + k] = s.q[k];
+    }
     bool coll = robot_pass<TASK, GEOM>(M, s.q, row + 6, O, hv, true, ee, dist, scratch, cs);
+    URGYM_WARP_SYNC();      // every lane is done with the scratch before observation rows are written over it
     // 4. observation: carries link_dist from BEFORE this step's reward (quirk Q1)               core.py:311
     write_obs_row<TASK>(row, ee, s.q, s.E, O, vel, s.ld);
     // 5. termination                                                                           core.py:313-315

@@ -25,6 +25,9 @@
 using namespace urgym;
 
 #define URGYM_BLOCK 128
+#ifndef URGYM_STEP_MINBLOCKS
+#define URGYM_STEP_MINBLOCKS 6      /* resident step-kernel blocks per SM the register allocation is held to */
+#endif
 #define URGYM_STAT_SLOTS 64
 #define URGYM_RETURN_SCALE 65536.0f     /* episode returns are summed in 2^-16 fixed point: order-independent */
 
@@ -101,8 +104,12 @@ template <int GEOM> __device__ __forceinline__ const float4 *stage_hull(const fl
     for (int i = threadIdx.x; i < UR5E_NUM_HULL_VERTS; i += blockDim.x) s[i] = g[i];
     return s;
 }
+// per-warp tile: 32 observation rows, 32 action rows; the capsule pass's scratch column block [41][32] overlays it
+template <int TASK> struct TileFloats {
+    static constexpr int value = (Traits<TASK>::OBS + 6) > URGYM_SCRATCH_FLOATS ? (Traits<TASK>::OBS + 6) : URGYM_SCRATCH_FLOATS;
+};
 template <int TASK, int GEOM> constexpr size_t step_smem_bytes() {
-    return (size_t)URGYM_BLOCK * (Traits<TASK>::OBS + 6 + (GEOM == GEOM_CAPSULE ? URGYM_SCRATCH_FLOATS : 0)) * sizeof(float) +
+    return (size_t)URGYM_BLOCK * TileFloats<TASK>::value * sizeof(float) +
            (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
 
@@ -112,14 +119,13 @@ template <int TASK, int GEOM> constexpr size_t step_smem_bytes() {
 // Finished envs are NOT reset here: the step only raises their terminated / truncated flags, and the auto-reset
 // kernel that follows in the stream handles them in dense form.
 template <int TASK, int GEOM>
-__global__ void __launch_bounds__(URGYM_BLOCK) urgym_step_kernel(const __grid_constant__ ModelConst c_model, const StepArgs A) {
+__global__ void __launch_bounds__(URGYM_BLOCK, URGYM_STEP_MINBLOCKS) urgym_step_kernel(const __grid_constant__ ModelConst c_model, const StepArgs A) {
     typedef Traits<TASK> TT;
     constexpr int D = TT::OBS, G = TT::GOAL, B = URGYM_BLOCK, W = 32;
+    constexpr int TF = TileFloats<TASK>::value;
     extern __shared__ float4 smem4[];
-    float *s_obs_all = reinterpret_cast<float *>(smem4);      // [B][D]
-    float *s_act_all = s_obs_all + B * D;                     // [B][6]
-    float *s_scr_all = s_act_all + B * 6;                     // [warps][URGYM_SCRATCH_FLOATS][32] (capsule geometry)
-    float4 *s_hull = reinterpret_cast<float4 *>(s_scr_all + (GEOM == GEOM_CAPSULE ? B * URGYM_SCRATCH_FLOATS : 0));
+    float *s_tiles = reinterpret_cast<float *>(smem4);        // [warps][32 * TF]: obs tile [32][D], then action tile [32][6]
+    float4 *s_hull = reinterpret_cast<float4 *>(s_tiles + B * TF);
     __shared__ unsigned long long s_stats[URGYM_STATS_COUNT];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -130,7 +136,8 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_step_kernel(const __grid_co
 
     const int64_t wbase = (int64_t)blockIdx.x * B + warp * W;                 // first env of this warp
     const int rows = (A.n - wbase) < W ? (int)max((long long)(A.n - wbase), 0ll) : W;
-    float *s_obs = s_obs_all + warp * W * D, *s_act = s_act_all + warp * W * 6;
+    float *s_obs = s_tiles + warp * W * TF, *s_act = s_obs + W * D;
+    float *s_scr = s_obs + lane;                              // capsule scratch: column `lane` of a [41][32] block
 
     // action tile: 16-byte vectorised, coalesced
     if (rows > 0) {
@@ -145,27 +152,30 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_step_kernel(const __grid_co
     }
     __syncwarp();
 
-    const int64_t i = wbase + lane;
-    if (lane < rows) {
+    if (rows > 0) {
+        // every lane runs the step (warp-level barriers inside); lanes past the end redo the last env and store nothing
+        const bool live = lane < rows;
+        const int64_t i = wbase + (live ? lane : rows - 1);
         EnvState s;
         StepOut o;
         float vel[6];
         load_dyn<TASK>(A.st, i, s);
         load_E<TASK>(A.st, i, s.E);
-        env_step<TASK, GEOM>(c_model, s, s_act + lane * 6, hv, s_obs + lane * D, o, vel,
-                             s_scr_all + warp * W * URGYM_SCRATCH_FLOATS + lane, W);
-        store_dyn<TASK>(A.st, i, s);
-        A.rew[i] = o.reward;
-        A.term[i] = o.terminated ? 1 : 0;
-        A.trunc[i] = o.truncated ? 1 : 0;
-        A.succ[i] = o.success ? 1 : 0;
-        if (o.terminated || o.truncated) {
-            atomicAdd(&s_stats[0], 1ull);
-            atomicAdd(&s_stats[1], (unsigned long long)__float2ll_rn(s.ep_ret * URGYM_RETURN_SCALE));
-            atomicAdd(&s_stats[2], (unsigned long long)s.elapsed);
-            if (o.success) atomicAdd(&s_stats[3], 1ull);
-            if (o.collision) atomicAdd(&s_stats[4], 1ull);
-            if (o.truncated && !o.terminated) atomicAdd(&s_stats[5], 1ull);
+        env_step<TASK, GEOM>(c_model, s, s_act + (live ? lane : rows - 1) * 6, hv, s_obs + lane * D, o, vel, s_scr, W);
+        if (live) {
+            store_dyn<TASK>(A.st, i, s);
+            A.rew[i] = o.reward;
+            A.term[i] = o.terminated ? 1 : 0;
+            A.trunc[i] = o.truncated ? 1 : 0;
+            A.succ[i] = o.success ? 1 : 0;
+            if (o.terminated || o.truncated) {
+                atomicAdd(&s_stats[0], 1ull);
+                atomicAdd(&s_stats[1], (unsigned long long)__float2ll_rn(s.ep_ret * URGYM_RETURN_SCALE));
+                atomicAdd(&s_stats[2], (unsigned long long)s.elapsed);
+                if (o.success) atomicAdd(&s_stats[3], 1ull);
+                if (o.collision) atomicAdd(&s_stats[4], 1ull);
+                if (o.truncated && !o.terminated) atomicAdd(&s_stats[5], 1ull);
+            }
         }
     }
     __syncwarp();
@@ -214,7 +224,8 @@ struct AuxArgs {
     const float4 *hull;
 };
 
-#define URGYM_RESET_GROUP 128       /* envs scanned by one warp of the reset kernel */
+#define URGYM_RESET_GROUP 512       /* envs scanned by one warp of the reset kernel: ~20 finished envs at a 4 % done
+                                       rate, so the lane-per-env phase runs with most lanes busy */
 
 // RobotTaskEnv.reset for the envs selected by the masks (core.py:263-273), in dense form: every warp scans 128
 // consecutive envs, compacts the selected ones with warp ballots, and resets them 32 at a time, one env per lane.
