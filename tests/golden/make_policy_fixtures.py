@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Extract the ACTOR weights of the reference's shipped SAC policies (data, not source) and the closed-loop numbers the
+reference publishes for them, as fixtures for the closed-loop check.
+
+Run in the build container (where /root/reference is mounted); outputs are committed because the GPU box has no
+reference:   python tests/golden/make_policy_fixtures.py  ->  tests/golden/policy_{Ori,Obs,Sta,Dyn}.npz
+
+Sources (reference file): Trained_Models/Trained_*/best_model.zip:policy.pth (SB3 SAC MultiInputPolicy actor:
+features = concat(achieved_goal, desired_goal, observation) -> Linear 256 -> ReLU -> Linear 256 -> ReLU -> mu -> tanh),
+Trained_Models/Trained_{Ori,Obs,Sta}/best.txt:1-2 and Trained_Models/Trained_Dyn/best_modeltest_result.txt:1-2
+(success rate and mean episode reward over the model_test.py scenarios)."""
+import io
+import os
+import re
+import sys
+import zipfile
+
+import numpy as np
+import torch
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+RESULT = {"Ori": "best.txt", "Obs": "best.txt", "Sta": "best.txt", "Dyn": "best_modeltest_result.txt"}
+
+for t in ("Ori", "Obs", "Sta", "Dyn"):
+    d = os.path.join(REF, "Trained_Models", f"Trained_{t}")
+    z = zipfile.ZipFile(os.path.join(d, "best_model.zip"))
+    sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=False)
+    out = {k.replace("actor.", "").replace(".", "_"): v.numpy().astype(np.float32) for k, v in sd.items()
+           if k.startswith("actor.") and "log_std" not in k}
+    lines = open(os.path.join(d, RESULT[t])).read().splitlines()
+    out["published_success_rate_pct"] = np.float64(re.search(r"([-\d.]+)%", lines[0]).group(1))
+    out["published_mean_reward"] = np.float64(re.search(r"is ([-\d.]+)", lines[1]).group(1))
+    eps = np.array([[float(x) for x in l.replace(" ", "").split(",")] for l in lines[2:] if l.strip()])
+    out["published_episodes"] = np.int64(len(eps))
+    out["published_mean_steps"] = np.float64(eps[:, 2].mean())
+    np.savez_compressed(os.path.join(HERE, f"policy_{t}.npz"), **out)
+    print(t, {k: (v.shape if getattr(v, "shape", ()) else float(v)) for k, v in out.items()})
