@@ -39,9 +39,9 @@ GEOM_HULL, GEOM_CAPSULE = 0, 1
 
 
 def build_oracle(force: bool = False) -> str:
-    src = os.path.join(_HERE, "ur_oracle_sim.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-C", _HERE])
+    if force and os.path.exists(_LIB_PATH):
+        os.remove(_LIB_PATH)
+    subprocess.check_call(["make", "-s", "-C", _HERE])        # no-op when up to date (sources + generated headers)
     return _LIB_PATH
 
 
@@ -63,6 +63,7 @@ def lib():
         _lib.orc_target_obstacle_distance.restype = ctypes.c_double
         _lib.orc_pair_distance.restype = ctypes.c_double
         _lib.orc_set_flags.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int]
+        _lib.orc_set_capsule_fit.argtypes = [ctypes.POINTER(ctypes.c_double)] * 3 + [ctypes.c_double]
     return _lib
 
 
@@ -324,6 +325,12 @@ class OracleSim:
     def all_pair_distances(self) -> np.ndarray:
         out = _d(24)
         lib().orc_check_collision(ctypes.byref(self._scene()), out)
+        return np.array(out[:])
+
+    def capsule_core_distances(self) -> np.ndarray:
+        """segment-core distances of the 24 pairs (capsule geometry without its pair margins): calibration input"""
+        out = _d(24)
+        lib().orc_capsule_core_distances(ctypes.byref(self._scene()), out)
         return np.array(out[:])
 
     def get_target_to_obstacle_distance(self) -> float:            # pyb_setup.py:431-437

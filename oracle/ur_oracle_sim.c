@@ -45,6 +45,7 @@
 #include <stdlib.h>
 
 #include "../ur-gym_b200/csrc/ur5e_model_data.h"
+#include "../ur-gym_b200/csrc/urgym_capsule_fit.h"
 
 #define ORC_GEOM_HULL 0
 #define ORC_GEOM_CAPSULE 1
@@ -58,6 +59,24 @@ typedef struct {
 } orc_flags_t;
 
 static orc_flags_t g_flags = {0, 0.001, 1e-13, 2000};
+
+/* capsule geometry: what is subtracted from the distance between the segment cores, per pair class (defaults from the
+ * generated urgym_capsule_fit.h; oracle/calibrate_capsules.py overrides them while fitting) */
+static double g_fit_obst[7], g_fit_box[7], g_fit_self[9], g_fit_obst_h;
+static int g_fit_init = 0;
+static void fit_init(void) {
+    if (g_fit_init) return;
+    for (int i = 0; i < 7; i++) { g_fit_obst[i] = URGYM_FIT_OBST[i]; g_fit_box[i] = URGYM_FIT_BOX[i]; }
+    for (int i = 0; i < 9; i++) g_fit_self[i] = URGYM_FIT_SELF[i];
+    g_fit_obst_h = URGYM_FIT_OBST_H;
+    g_fit_init = 1;
+}
+void orc_set_capsule_fit(const double obst[7], const double box[7], const double self[9], double obst_h) {
+    for (int i = 0; i < 7; i++) { g_fit_obst[i] = obst[i]; g_fit_box[i] = box[i]; }
+    for (int i = 0; i < 9; i++) g_fit_self[i] = self[i];
+    g_fit_obst_h = obst_h;
+    g_fit_init = 1;
+}
 
 void orc_set_flags(int prim_margin_mode, double hull_margin, double gjk_rel_tol, int gjk_max_iter) {
     g_flags.prim_margin_mode = prim_margin_mode;
@@ -426,10 +445,12 @@ static void make_table(shape_t *s) { make_box(s, 0.5, 0.0, -0.12 - 0.46, 0.55, 0
 static void make_track(shape_t *s) { make_box(s, 0.0, 0.0, -0.06, 0.1, 0.55, 0.06); }
 
 /* obstacle: cylinder radius 0.05, height 0.4, axis = local z    reach.py:279-283,427-431,626-630 */
-static const double g_obst_cap_verts[6] = {0, 0, -0.2, 0, 0, 0.2};
+static double g_obst_cap_verts[6] = {0, 0, -0.2, 0, 0, 0.2};
 static void make_obstacle(const orc_scene_t *sc, shape_t *s) {
     if (sc->geom == ORC_GEOM_CAPSULE) {
-        s->type = SH_HULL; s->verts = g_obst_cap_verts; s->nverts = 2; s->margin = 0.05;
+        fit_init();
+        g_obst_cap_verts[2] = -g_fit_obst_h; g_obst_cap_verts[5] = g_fit_obst_h;
+        s->type = SH_HULL; s->verts = g_obst_cap_verts; s->nverts = 2; s->margin = 0.0;   /* pair margins: cap_pair_margin */
         quat_to_mat(sc->obs_quat, s->R); memcpy(s->t, sc->obs_pos, 3 * sizeof(double));
         return;
     }
@@ -443,7 +464,7 @@ static void make_target(const orc_scene_t *sc, shape_t *s) {
     if (sc->geom == ORC_GEOM_CAPSULE) {
         static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         s->type = SH_POINT; memcpy(s->R, I, sizeof(I));
-        s->margin = sc->tgt_type == 1 ? 0.02 : 0.025 * sqrt(3.0);
+        s->margin = (sc->tgt_type == 1 ? 0.02 : 0.025 * sqrt(3.0)) + 0.05;     /* target sphere + obstacle radius */
         memcpy(s->t, sc->tgt_pos, 3 * sizeof(double));
         return;
     }
@@ -471,7 +492,7 @@ static void make_link(const orc_scene_t *sc, int link, double pos[7][3], double 
                 }
             g_cap_init = 1;
         }
-        s->verts = g_cap_verts[link]; s->nverts = 2; s->margin = UR5E_CAPSULE_R[link] + g_flags.hull_margin;
+        s->verts = g_cap_verts[link]; s->nverts = 2; s->margin = 0.0;     /* pair margins: cap_pair_margin */
     } else {
         s->verts = &UR5E_HULL_VERTS[3 * UR5E_HULL_OFFSET[link]];
         s->nverts = UR5E_HULL_OFFSET[link + 1] - UR5E_HULL_OFFSET[link];
@@ -480,6 +501,13 @@ static void make_link(const orc_scene_t *sc, int link, double pos[7][3], double 
     memcpy(s->R, rot[link], 9 * sizeof(double)); memcpy(s->t, pos[link], 3 * sizeof(double));
 }
 
+/* capsule geometry: margin of a pair class.  kind 0 = link vs obstacle, 1 = link vs table/track, 2 = self pair index */
+static double cap_pair_margin(int kind, int l, int p) {
+    fit_init();
+    if (kind == 0) return g_fit_obst[l];
+    if (kind == 1) return g_fit_box[l];
+    return g_fit_self[p];
+}
 static double pair_distance(const shape_t *A, const shape_t *B, int *deep) {
     int dp = 0;
     double d = gjk_core_distance(A, B, &dp, 0);
@@ -496,6 +524,7 @@ int orc_link_distances(const orc_scene_t *sc, double out[5]) {
         int dp = 0;
         make_link(sc, i + 2, pos, rot, &L);
         out[i] = pair_distance(&L, &O, &dp);
+        if (sc->geom == ORC_GEOM_CAPSULE) out[i] -= cap_pair_margin(0, i + 2, 0);
         if (dp) deep |= (1 << i);
     }
     return deep;
@@ -517,6 +546,7 @@ int orc_check_collision(const orc_scene_t *sc, double *all_out) {
         for (int l = 2; l < 7; l++) {
             make_link(sc, l, pos, rot, &L);
             double d = pair_distance(&L, &T, 0);
+            if (sc->geom == ORC_GEOM_CAPSULE) d -= cap_pair_margin(0, l, 0);
             if (all_out) all_out[idx] = d;
             if (d <= thr && !first) { first = 1 + idx; if (!all_out) return first; }
             idx++;
@@ -530,6 +560,7 @@ int orc_check_collision(const orc_scene_t *sc, double *all_out) {
         for (int l = 2; l < 7; l++) {
             make_link(sc, l, pos, rot, &L);
             double d = pair_distance(&L, &T, 0);
+            if (sc->geom == ORC_GEOM_CAPSULE) d -= cap_pair_margin(1, l, 0);
             if (all_out) all_out[idx] = d;
             if (d <= thr && !first) { first = 1 + idx; if (!all_out) return first; }
             idx++;
@@ -540,6 +571,7 @@ int orc_check_collision(const orc_scene_t *sc, double *all_out) {
         for (int b = start; b < 7; b++) {
             make_link(sc, a, pos, rot, &L); make_link(sc, b, pos, rot, &M);
             double d = pair_distance(&L, &M, 0);
+            if (sc->geom == ORC_GEOM_CAPSULE) d -= cap_pair_margin(2, 0, idx - 15);
             if (all_out) all_out[idx] = d;
             if (d <= thr && !first) { first = 1 + idx; if (!all_out) return first; }
             idx++;
@@ -567,6 +599,20 @@ double orc_pair_distance(const orc_scene_t *sc, int link, int other, int *deep, 
     double d = gjk_core_distance(&L, &O, &dp, iters) - L.margin - O.margin;
     if (deep) *deep = dp;
     return d;
+}
+
+/* calibration helper: the 24 pair distances of orc_check_collision between the SEGMENT CORES (no pair margins; the box
+ * pairs keep the box margin), for the current capsule-fit obstacle half length */
+void orc_capsule_core_distances(const orc_scene_t *sc_in, double out[24]) {
+    orc_scene_t sc = *sc_in;
+    sc.geom = ORC_GEOM_CAPSULE;
+    double so[7], sb[7], ss[9], sh;
+    fit_init();
+    memcpy(so, g_fit_obst, sizeof(so)); memcpy(sb, g_fit_box, sizeof(sb)); memcpy(ss, g_fit_self, sizeof(ss)); sh = g_fit_obst_h;
+    double z7[7] = {0}, z9[9] = {0};
+    orc_set_capsule_fit(z7, z7, z9, sh);
+    orc_check_collision(&sc, out);
+    orc_set_capsule_fit(so, sb, ss, sh);
 }
 
 int orc_scene_sizeof(void) { return (int)sizeof(orc_scene_t); }

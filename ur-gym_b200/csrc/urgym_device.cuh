@@ -111,7 +111,10 @@ struct ModelConst {
     float cap_m[7];             // capsule margin = bounding radius + hull_margin (so capsule distance <= hull distance)
     float cap_hl[7];            // half length of the capsule segment (+ round-off allowance), for the sphere broad phase
     float cap_ia[7];            // 1 / |segment|^2
-    float obst_cap_ie;          // 1 / |obstacle capsule segment|^2
+    float obst_cap_ie;          // 1 / |obstacle capsule segment|^2 (bounding capsule, hull-mode broad phase)
+    // capsule geometry proper (urgym_capsule_fit.h): calibrated against the hull geometry
+    float fit_obst[7], fit_box[7], fit_self[9];
+    float fit_obst_h, fit_obst_ie;
     float box_top;              // highest top face of the table / track cores (z), for the height broad phase
     int hull_off[8];            // vertex ranges of links 0..6 inside the packed float4 vertex array
     // margins of Bullet's GJK pair detector (distance = |core gap| - marginA - marginB)

@@ -175,11 +175,12 @@ template <> struct LinkShape<GEOM_CAPSULE> {
         a = f3(M.neutral_ca[l][0], M.neutral_ca[l][1], M.neutral_ca[l][2]);
         b = f3(M.neutral_cb[l][0], M.neutral_cb[l][1], M.neutral_cb[l][2]);
     }
-    // getClosestPoints(UR5, obstacle, linkIndexA=l)[0][8]                              pyb_setup.py:439-456
+    // getClosestPoints(UR5, obstacle, linkIndexA=l)[0][8], capsule geometry                 pyb_setup.py:439-456
     URGYM_HD float obstacle_dist(const ModelConst &M, int l, const ObstW &O) const {
-        float3 oa = O.c - M.obst_cap_h * O.u, ob = O.c + M.obst_cap_h * O.u;
-        return sqrtf(segseg_dist2(a, b, oa, ob)) - M.cap_m[l] - M.obst_cap_m;
+        float3 oa = O.c - M.fit_obst_h * O.u, ob = O.c + M.fit_obst_h * O.u;
+        return sqrtf(segseg_dist2(a, b, oa, ob)) - M.fit_obst[l];
     }
+    // the methods below use the BOUNDING capsules: they are the exact-safe broad phase of the hull geometry
     // box 0 = table, 1 = track
     URGYM_HD bool box_hit(const ModelConst &M, int l, int box) const {
         float margin = M.box_margin[box];
@@ -254,7 +255,7 @@ template <int TASK, int GEOM>
 URGYM_HD float target_obstacle_dist(const ModelConst &M, const float *goal, const ObstW &O) {
     float3 g = f3(goal[0], goal[1], goal[2]);
     if (GEOM == GEOM_CAPSULE) {
-        float3 oa = O.c - M.obst_cap_h * O.u, ob = O.c + M.obst_cap_h * O.u;
+        float3 oa = O.c - M.fit_obst_h * O.u, ob = O.c + M.fit_obst_h * O.u;
         return sqrtf(point_seg_dist2(g, oa, ob)) - M.tgt_cap_m[TASK] - M.obst_cap_m;
     }
     CylW C; C.c = O.c; C.u = O.u; C.r = M.obst_r; C.h = M.obst_h;
@@ -330,14 +331,14 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
     if (!collide) return false;
     bool hit = false;
     // links 2..6 vs obstacle (distances kept: they are get_link_distances' values), table and track
-    const float3 oa = O.c - M.obst_cap_h * O.u, ob = O.c + M.obst_cap_h * O.u;
+    const float3 oa = O.c - M.fit_obst_h * O.u, ob = O.c + M.fit_obst_h * O.u;
 #pragma unroll 1
     for (int l = 2; l < 7; l++) {
         const float *c = cap + (l - 1) * 6 * cs;
         const float3 a = f3(c[0], c[cs], c[2 * cs]), b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
-        const float m = M.cap_m[l];
+        const float m = M.fit_box[l];
         if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
-            float d = sqrtf(segseg_dist2_fast(a, b, oa, ob, M.cap_ia[l], M.obst_cap_ie)) - m - M.obst_cap_m;
+            float d = sqrtf(segseg_dist2_fast(a, b, oa, ob, M.cap_ia[l], M.fit_obst_ie)) - M.fit_obst[l];
             hit = hit || (d <= URGYM_COLLISION_MARGIN);
             cap[(36 + l - 2) * cs] = d;
         }
@@ -362,7 +363,7 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
         const float *c1 = cap + (l1 - 1) * 6 * cs, *c2 = cap + (l2 - 1) * 6 * cs;
         const float3 a1 = f3(c1[0], c1[cs], c1[2 * cs]), b1 = f3(c1[3 * cs], c1[4 * cs], c1[5 * cs]);
         const float3 a2 = f3(c2[0], c2[cs], c2[2 * cs]), b2 = f3(c2[3 * cs], c2[4 * cs], c2[5 * cs]);
-        const float reach = URGYM_COLLISION_MARGIN + M.cap_m[l1] + M.cap_m[l2];
+        const float reach = URGYM_COLLISION_MARGIN + M.fit_self[p];
         const float3 dm = 0.5f * ((a1 + b1) - (a2 + b2));
         const float far = reach + M.cap_hl[l1] + M.cap_hl[l2];
         if (dot(dm, dm) <= far * far)       // sphere broad phase (exact bound)

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "ur5e_model_data.h"
+#include "urgym_capsule_fit.h"
 #include "urgym_device.cuh"
 
 namespace urgym {
@@ -67,6 +68,10 @@ static void build_model_const(ModelConst &M) {
     // target: the Obs sphere itself, the bounding sphere of the Sta/Dyn cube
     M.obst_cap_h = 0.2f; M.obst_cap_m = 0.05f;
     M.obst_cap_ie = (float)(1.0 / (0.4 * 0.4));
+    for (int l = 0; l < 7; l++) { M.fit_obst[l] = (float)URGYM_FIT_OBST[l]; M.fit_box[l] = (float)URGYM_FIT_BOX[l]; }
+    for (int k = 0; k < 9; k++) M.fit_self[k] = (float)URGYM_FIT_SELF[k];
+    M.fit_obst_h = (float)URGYM_FIT_OBST_H;
+    M.fit_obst_ie = (float)(1.0 / (4.0 * URGYM_FIT_OBST_H * URGYM_FIT_OBST_H));
     M.box_top = (float)fmax(tc[2] + th[2] - pm, kc[2] + kh[2] - pm);
     M.tgt_cap_m[0] = 0.0f; M.tgt_cap_m[1] = 0.02f;
     M.tgt_cap_m[2] = M.tgt_cap_m[3] = (float)(0.025 * 1.7320508075688772);
