@@ -129,7 +129,10 @@ def run_parity(sim, env_id, geom, n, steps, seed, offset=0, action_scale=1.2, rn
                 assert lin <= POS_TOL and ang <= ANG_TOL, ("obs", env_id, i, t, lin, ang, got_obs, o["observation"])
                 stats["max_lin"], stats["max_ang"] = max(stats["max_lin"], lin), max(stats["max_ang"], ang)
                 stats["max_q"] = max(stats["max_q"], np.abs(got_obs[6:12] - o["observation"][6:12]).max())
-            rel = max(0.0, abs(float(out["reward"][i]) - r) - rew_atol) / max(1.0, abs(r))
+            # 1e-5 relative to the size of the reward's TERMS: -100 d (Obs) / -70 d - 30 ang and w_i * (link_dist change)
+            # partly cancel, so a reward of -7 can be the difference of terms of size 50
+            scale = max(1.0, abs(r), 100.0 * float(oe.distance(o["achieved_goal"], e.task.get_goal())[0]))
+            rel = max(0.0, abs(float(out["reward"][i]) - r) - rew_atol) / scale
             if rel > REW_RTOL and not (e.task.kind == "Obs" and getattr(e.sim, "last_deep_mask", 0)):
                 # (Obs keeps the link-distance term on a colliding step; with interpenetrating cores the oracle's
                 # distance is a placeholder -- Bullet would run EPA there -- so that reward is not compared)
