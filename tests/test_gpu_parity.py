@@ -197,8 +197,9 @@ def test_state_roundtrip_and_checkpoint(ug):
         ug.UR5VecEnv("UR5OriReach-v1", 8).get_state("obstacle")
 
 
-def test_host_buffer_entry_point_matches_device_path(ug):
-    env_id, n = "UR5ObsReach-v1", 5000
+@pytest.mark.parametrize("n", [5000, 600_000])       # 600 k: the chunked three-stream pipeline (8 chunks)
+def test_host_buffer_entry_point_matches_device_path(ug, n):
+    env_id = "UR5ObsReach-v1"
     d_env, h_env = ug.UR5VecEnv(env_id, n, seed=4), ug.UR5VecEnv(env_id, n, seed=4)
     d_env.reset(); h_env.reset()
     buf = h_env.alloc_host_buffers()

@@ -86,6 +86,8 @@ struct urgym_env {
     int64_t launches;
     // staging for the host-buffer entry points
     cudaStream_t hstream;
+    cudaStream_t cstream[3];        // chunk pipeline of the host-buffer entry point
+    cudaEvent_t ev_fork, ev_join[3];
     void *dstage;
     size_t dstage_bytes;
     char err[512];
@@ -191,6 +193,12 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
             if ((e = cudaMemcpy(h->hull, hv, sizeof(hv), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
         }
         if ((e = cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
+        for (int k = 0; k < 3 && e == cudaSuccess; k++) {
+            e = cudaStreamCreateWithFlags(&h->cstream[k], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+        if (e != cudaSuccess) { rc = URGYM_ECUDA; break; }
     } while (0);
     if (rc != URGYM_OK) {
         fail(nullptr, rc, "urgym_create: %s", cudaGetErrorString(e));
@@ -207,6 +215,11 @@ extern "C" int urgym_destroy(urgym_env_t *h) {
     if (!h) return URGYM_EINVAL;
     cudaSetDevice(h->device);
     if (h->hstream) cudaStreamDestroy(h->hstream);
+    for (int k = 0; k < 3; k++) {
+        if (h->cstream[k]) cudaStreamDestroy(h->cstream[k]);
+        if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->dstage) cudaFree(h->dstage);
     if (h->hull) cudaFree(h->hull);
     if (h->pool) cudaFree(h->pool);
@@ -240,6 +253,43 @@ extern "C" int urgym_set_event(urgym_env_t *h, uint32_t event) {
     return URGYM_OK;
 }
 
+static StateView view_at(const StateView &v, int64_t off) {
+    StateView o = v;
+    o.qa += off; o.qb += off; o.ld4 += off; o.ld1 += off;
+    for (int g = 0; g < 4; g++) o.e4[g] += off;
+    o.e2 += off; o.e1 += off; o.va += off; o.vb += off;
+    return o;
+}
+
+// one env step of the envs [first, first + count) (array pointers are those of the WHOLE arrays)
+static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, const float *actions, float *obs, float *achieved,
+                      float *desired, float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
+                      float *terminal_obs, float *terminal_achieved, cudaStream_t stream) {
+    const int D = obs_dim(h->task), G = goal_dim(h->task);
+    StepArgs A;
+    A.st = view_at(h->st, first); A.n = count;
+    A.actions = actions + first * 6; A.obs = obs + first * D;
+    A.ach = achieved ? achieved + first * G : nullptr; A.des = desired ? desired + first * G : nullptr;
+    A.rew = reward + first; A.term = terminated + first; A.trunc = truncated + first; A.succ = is_success + first;
+    A.stats = h->stats; A.event = h->d_event; A.bump = bump; A.hull = h->hull;
+    CK(k_step[h->geom][h->task](h->model, A, stream));
+    h->launches++;
+    if (h->autoreset) {
+        // the finished envs (terminated | truncated) restart in a second, dense kernel
+        AuxArgs R;
+        memset(&R, 0, sizeof(R));
+        R.st = A.st; R.n = count; R.offset = h->offset + first; R.key = key_of(h->seed);
+        R.mask = A.term; R.mask2 = A.trunc; R.autoreset = 1;
+        R.obs = A.obs; R.ach = A.ach; R.des = A.des;
+        R.tobs = terminal_obs ? terminal_obs + first * D : nullptr;
+        R.tach = terminal_achieved ? terminal_achieved + first * G : nullptr;
+        R.stats = h->stats; R.event = h->d_event; R.hull = h->hull;
+        CK(k_reset[h->geom][h->task](h->model, R, stream));
+        h->launches++;
+    }
+    return URGYM_OK;
+}
+
 extern "C" int urgym_step(urgym_env_t *h, const float *actions, float *obs, float *achieved, float *desired,
                           float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
                           float *terminal_obs, float *terminal_achieved, void *stream) {
@@ -247,25 +297,8 @@ extern "C" int urgym_step(urgym_env_t *h, const float *actions, float *obs, floa
     if (!actions || !obs || !reward || !terminated || !truncated || !is_success)
         return fail(h, URGYM_EINVAL, "urgym_step: actions, obs, reward, terminated, truncated, is_success must not be NULL%s", "");
     CK(cudaSetDevice(h->device));
-    StepArgs A;
-    A.st = h->st; A.n = h->n;
-    A.actions = actions; A.obs = obs; A.ach = achieved; A.des = desired; A.rew = reward;
-    A.term = terminated; A.trunc = truncated; A.succ = is_success;
-    A.stats = h->stats; A.event = h->d_event; A.hull = h->hull;
-    CK(k_step[h->geom][h->task](h->model, A, (cudaStream_t)stream));
-    h->launches++;
-    if (h->autoreset) {
-        // the finished envs (terminated | truncated) restart in a second, dense kernel
-        AuxArgs R;
-        memset(&R, 0, sizeof(R));
-        R.st = h->st; R.n = h->n; R.offset = h->offset; R.key = key_of(h->seed);
-        R.mask = terminated; R.mask2 = truncated; R.autoreset = 1;
-        R.obs = obs; R.ach = achieved; R.des = desired; R.tobs = terminal_obs; R.tach = terminal_achieved;
-        R.stats = h->stats; R.event = h->d_event; R.hull = h->hull;
-        CK(k_reset[h->geom][h->task](h->model, R, (cudaStream_t)stream));
-        h->launches++;
-    }
-    return URGYM_OK;
+    return step_range(h, 0, h->n, 1, actions, obs, achieved, desired, reward, terminated, truncated, is_success,
+                      terminal_obs, terminal_achieved, (cudaStream_t)stream);
 }
 
 extern "C" int urgym_reset(urgym_env_t *h, const uint8_t *mask, float *obs, float *achieved, float *desired, void *stream) {
@@ -377,23 +410,39 @@ extern "C" int urgym_step_host(urgym_env_t *h, const float *actions, float *obs,
     uint8_t *d_term = (uint8_t *)p; p += b_f;
     uint8_t *d_trunc = (uint8_t *)p; p += b_f;
     uint8_t *d_succ = (uint8_t *)p; p += b_f;
-    cudaStream_t s = h->hstream;
-    CK(cudaMemcpyAsync(d_act, actions, n * 6 * 4, cudaMemcpyHostToDevice, s));
-    rc = urgym_step(h, d_act, d_obs, achieved ? d_ach : nullptr, desired ? d_des : nullptr, d_rew, d_term, d_trunc, d_succ,
-                    terminal_obs ? d_tobs : nullptr, terminal_achieved ? d_tach : nullptr, s);
-    if (rc != URGYM_OK) return rc;
-    CK(cudaMemcpyAsync(obs, d_obs, n * D * 4, cudaMemcpyDeviceToHost, s));
-    if (achieved) CK(cudaMemcpyAsync(achieved, d_ach, n * G * 4, cudaMemcpyDeviceToHost, s));
-    if (desired) CK(cudaMemcpyAsync(desired, d_des, n * G * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(reward, d_rew, n * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(terminated, d_term, n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(truncated, d_trunc, n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(is_success, d_succ, n, cudaMemcpyDeviceToHost, s));
-    // terminal rows are meaningful only where the env finished; the whole arrays are copied (rows of running envs
-    // keep whatever the staging buffer held)
-    if (terminal_obs) CK(cudaMemcpyAsync(terminal_obs, d_tobs, n * D * 4, cudaMemcpyDeviceToHost, s));
-    if (terminal_achieved) CK(cudaMemcpyAsync(terminal_achieved, d_tach, n * G * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    // Chunk pipeline over three streams: while chunk k steps, chunk k+1's actions travel host->device and chunk k-1's
+    // results travel device->host (the copy engines work in both directions at once).  Chunks are multiples of the
+    // reset kernel's 256-env groups; the reset event is bumped once, before the fork.
+    const int64_t N = h->n;
+    int64_t chunk = ((N / 8 + 255) / 256) * 256;
+    if (chunk < 65536) chunk = N;                       // small batches: one chunk
+    cudaStream_t s0 = h->hstream;
+    urgym_bump_kernel<<<1, 1, 0, s0>>>(h->d_event);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaEventRecord(h->ev_fork, s0));
+    int used = 0, k = 0;
+    for (int64_t first = 0; first < N; first += chunk, k++) {
+        const int64_t cnt = (N - first) < chunk ? (N - first) : chunk;
+        cudaStream_t s = h->cstream[k % 3];
+        if (k < 3) { CK(cudaStreamWaitEvent(s, h->ev_fork, 0)); used = k + 1; }
+        CK(cudaMemcpyAsync(d_act + first * 6, actions + first * 6, (size_t)cnt * 6 * 4, cudaMemcpyHostToDevice, s));
+        rc = step_range(h, first, cnt, 0, d_act, d_obs, achieved ? d_ach : nullptr, desired ? d_des : nullptr, d_rew, d_term,
+                        d_trunc, d_succ, terminal_obs ? d_tobs : nullptr, terminal_achieved ? d_tach : nullptr, s);
+        if (rc != URGYM_OK) return rc;
+        CK(cudaMemcpyAsync(obs + first * D, d_obs + first * D, (size_t)cnt * D * 4, cudaMemcpyDeviceToHost, s));
+        if (achieved) CK(cudaMemcpyAsync(achieved + first * G, d_ach + first * G, (size_t)cnt * G * 4, cudaMemcpyDeviceToHost, s));
+        if (desired) CK(cudaMemcpyAsync(desired + first * G, d_des + first * G, (size_t)cnt * G * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(reward + first, d_rew + first, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(terminated + first, d_term + first, (size_t)cnt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(truncated + first, d_trunc + first, (size_t)cnt, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(is_success + first, d_succ + first, (size_t)cnt, cudaMemcpyDeviceToHost, s));
+        // terminal rows are meaningful only where the env finished; the whole arrays are copied (rows of running envs
+        // keep whatever the staging buffer held)
+        if (terminal_obs) CK(cudaMemcpyAsync(terminal_obs + first * D, d_tobs + first * D, (size_t)cnt * D * 4, cudaMemcpyDeviceToHost, s));
+        if (terminal_achieved) CK(cudaMemcpyAsync(terminal_achieved + first * G, d_tach + first * G, (size_t)cnt * G * 4, cudaMemcpyDeviceToHost, s));
+    }
+    for (int j = 0; j < used; j++) CK(cudaStreamSynchronize(h->cstream[j]));
     return URGYM_OK;
 }
 

@@ -91,7 +91,8 @@ struct StepArgs {
     float *obs, *ach, *des, *rew;
     uint8_t *term, *trunc, *succ;
     unsigned long long *stats;
-    uint32_t *event;            // device-resident reset-event counter (bumped once per step launch)
+    uint32_t *event;            // device-resident reset-event counter
+    int bump;                   // 1: this launch starts reset event number *event + 1 (0 when a step is split in ranges)
     const float4 *hull;
 };
 
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK, URGYM_STEP_MINBLOCKS) urgym_step_
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < URGYM_STATS_COUNT) s_stats[tid] = 0ull;
-    if (blockIdx.x == 0 && tid == 0) *A.event += 1u;          // this launch is reset event number *A.event
+    if (A.bump && blockIdx.x == 0 && tid == 0) *A.event += 1u;    // this launch is reset event number *A.event
     const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
     __syncthreads();
 
