@@ -131,7 +131,8 @@ def run_parity(sim, env_id, geom, n, steps, seed, offset=0, action_scale=1.2, rn
                 stats["max_q"] = max(stats["max_q"], np.abs(got_obs[6:12] - o["observation"][6:12]).max())
             # 1e-5 relative to the size of the reward's TERMS: -100 d (Obs) / -70 d - 30 ang and w_i * (link_dist change)
             # partly cancel, so a reward of -7 can be the difference of terms of size 50
-            scale = max(1.0, abs(r), 100.0 * float(oe.distance(o["achieved_goal"], e.task.get_goal())[0]))
+            scale = max(1.0, abs(r), 100.0 * float(oe.distance(o["achieved_goal"], e.task.get_goal())[0])
+                        + 100.0 * float(np.abs(np.asarray(e.task.link_dist) - ld_before).sum()))
             rel = max(0.0, abs(float(out["reward"][i]) - r) - rew_atol) / scale
             if rel > REW_RTOL and not (e.task.kind == "Obs" and getattr(e.sim, "last_deep_mask", 0)):
                 # (Obs keeps the link-distance term on a colliding step; with interpenetrating cores the oracle's
