@@ -111,6 +111,7 @@ def run_parity(sim, env_id, geom, n, steps, seed, offset=0, action_scale=1.2, rn
         for i, e in enumerate(orc.envs):
             if not alive[i]:
                 continue
+            ld_before = np.array(e.task.last_dist, dtype=np.float64).copy()
             o, r, term, trunc, info = e.step(a[i])
             stats["steps"] += 1
             got_term, got_trunc, got_succ = bool(out["terminated"][i]), bool(out["truncated"][i]), bool(out["is_success"][i])
