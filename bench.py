@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--task", default="UR5DynReach-v1", choices=sorted(OBS_DIM))
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--geometry", default="capsule", choices=["capsule", "hull"])
+    ap.add_argument("--chains", type=int, default=2, help="independent env sub-ranges per GPU in the captured graph (1..4)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall-clock budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -45,7 +46,7 @@ def workload_config(args, world):
     return {"workload": f"{args.task}, {args.envs_per_gpu} envs per GPU, random actions U(-1,1) resident in HBM, "
                         f"auto-reset on, {args.geometry} geometry",
             "task": args.task, "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
-            "geometry": args.geometry, "sharding": f"env index ranges over {world} rank(s), no data-path collective",
+            "geometry": args.geometry, "chains_per_gpu": args.chains, "sharding": f"env index ranges over {world} rank(s), no data-path collective",
             "l2": "per-step traffic (state + actions + outputs) exceeds the 126 MB L2; an 8-deep ring of action buffers"}
 
 
@@ -185,7 +186,7 @@ def run_ours(args, rank, world, local_rank):
     for k in range(warm):
         env.step(ring[k % 8])
     # the timed loop replays a CUDA graph of 8 steps (one per action buffer of the ring): 16 kernels per replay
-    graph = env.capture_steps(ring)
+    graph = env.capture_steps(ring, chains=args.chains)
     graph.replay()
     env.stats(reset=True)
     steps = max(args.steps, 1)

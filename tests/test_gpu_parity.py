@@ -105,6 +105,31 @@ def test_sharding_invariance(ug):
     assert sw["episodes"] > 0 and sw["env_steps"] == n * 40
 
 
+@pytest.mark.parametrize("chains", [2, 3])
+def test_chained_graph_equals_plain_steps(ug, chains):
+    """a CUDA graph that advances env sub-ranges as independent chains == the same steps issued one by one"""
+    env_id, n, k = "UR5DynReach-v1", 50_000, 6
+    a_env, b_env = ug.UR5VecEnv(env_id, n, seed=13), ug.UR5VecEnv(env_id, n, seed=13)
+    a_env.reset(); b_env.reset()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    ring = [torch.rand((n, 6), device="cuda", generator=g) * 2 - 1 for _ in range(k)]
+    graph = b_env.capture_steps(ring, chains=chains)
+    for rep in range(4):
+        for a in ring:
+            a_env.step(a)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(a_env.obs, b_env.obs) and torch.equal(a_env.reward, b_env.reward)
+        assert torch.equal(a_env.terminated, b_env.terminated) and torch.equal(a_env.truncated, b_env.truncated)
+    for name in ("q", "goal", "obstacle", "obstacle_end", "link_dist", "elapsed", "ep_return"):
+        assert torch.equal(a_env.get_state(name), b_env.get_state(name)), name
+    sa, sb = a_env.stats(), b_env.stats()
+    assert sa == sb and sa["episodes"] > 0
+    # a whole-batch step after the chains keeps the event numbering consistent
+    a_env.step(ring[0]); b_env.step(ring[0])
+    assert torch.equal(a_env.obs, b_env.obs)
+
+
 def test_fused_autoreset_equals_explicit_reset(ug):
     """step with auto-reset == step without it followed by reset(mask = done) at the same reset event"""
     env_id, n = "UR5StaReach-v1", 4096

@@ -17,7 +17,7 @@ STATS_COUNT = 8
 STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions", "truncations", "env_steps",
               "reset_iterations")
 
-EXPORTS = ["urgym_create", "urgym_destroy", "urgym_last_error", "urgym_obs_dim", "urgym_goal_dim", "urgym_num_envs",
+EXPORTS = ["urgym_step_range", "urgym_create", "urgym_destroy", "urgym_last_error", "urgym_obs_dim", "urgym_goal_dim", "urgym_num_envs",
            "urgym_step", "urgym_reset", "urgym_observe", "urgym_refresh", "urgym_get_state", "urgym_set_state",
            "urgym_stats", "urgym_step_host", "urgym_reset_host", "urgym_set_autoreset", "urgym_get_event",
            "urgym_set_event", "urgym_set_seed", "urgym_launch_count"]
@@ -45,6 +45,7 @@ def lib():
         L.urgym_num_envs.argtypes = [vp]; L.urgym_num_envs.restype = i64
         L.urgym_step.argtypes = [vp] + [vp] * 10 + [vp]
         L.urgym_reset.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.urgym_step_range.argtypes = [vp, i64, i64, i32] + [vp] * 10 + [vp]
         L.urgym_observe.argtypes = [vp, vp, vp, vp, vp]
         L.urgym_refresh.argtypes = [vp, vp, vp]
         L.urgym_get_state.argtypes = [vp, i32, vp, vp]

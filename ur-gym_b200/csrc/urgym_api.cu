@@ -249,7 +249,9 @@ extern "C" int urgym_set_event(urgym_env_t *h, uint32_t event) {
     if (!h) return URGYM_EINVAL;
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(h->d_event, &event, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    uint32_t all[URGYM_MAX_CHAINS];
+    for (int c = 0; c < URGYM_MAX_CHAINS; c++) all[c] = event;
+    CK(cudaMemcpy(h->d_event, all, sizeof(all), cudaMemcpyHostToDevice));
     return URGYM_OK;
 }
 
@@ -262,7 +264,7 @@ static StateView view_at(const StateView &v, int64_t off) {
 }
 
 // one env step of the envs [first, first + count) (array pointers are those of the WHOLE arrays)
-static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, const float *actions, float *obs, float *achieved,
+static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, int chain, const float *actions, float *obs, float *achieved,
                       float *desired, float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
                       float *terminal_obs, float *terminal_achieved, cudaStream_t stream) {
     const int D = obs_dim(h->task), G = goal_dim(h->task);
@@ -271,7 +273,7 @@ static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, cons
     A.actions = actions + first * 6; A.obs = obs + first * D;
     A.ach = achieved ? achieved + first * G : nullptr; A.des = desired ? desired + first * G : nullptr;
     A.rew = reward + first; A.term = terminated + first; A.trunc = truncated + first; A.succ = is_success + first;
-    A.stats = h->stats; A.event = h->d_event; A.bump = bump; A.hull = h->hull;
+    A.stats = h->stats; A.event = h->d_event; A.bump = bump; A.chain = chain; A.hull = h->hull;
     CK(k_step[h->geom][h->task](h->model, A, stream));
     h->launches++;
     if (h->autoreset) {
@@ -283,11 +285,24 @@ static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, cons
         R.obs = A.obs; R.ach = A.ach; R.des = A.des;
         R.tobs = terminal_obs ? terminal_obs + first * D : nullptr;
         R.tach = terminal_achieved ? terminal_achieved + first * G : nullptr;
-        R.stats = h->stats; R.event = h->d_event; R.hull = h->hull;
+        R.stats = h->stats; R.event = h->d_event; R.chain = chain; R.hull = h->hull;
         CK(k_reset[h->geom][h->task](h->model, R, stream));
         h->launches++;
     }
     return URGYM_OK;
+}
+
+extern "C" int urgym_step_range(urgym_env_t *h, int64_t first, int64_t count, int chain, const float *actions, float *obs,
+                                float *achieved, float *desired, float *reward, uint8_t *terminated, uint8_t *truncated,
+                                uint8_t *is_success, float *terminal_obs, float *terminal_achieved, void *stream) {
+    if (!h) return URGYM_EINVAL;
+    if (!actions || !obs || !reward || !terminated || !truncated || !is_success)
+        return fail(h, URGYM_EINVAL, "urgym_step_range: actions, obs, reward, terminated, truncated, is_success must not be NULL%s", "");
+    if (first < 0 || count <= 0 || first + count > h->n || chain < 0 || chain >= URGYM_MAX_CHAINS)
+        return fail(h, URGYM_EINVAL, "urgym_step_range: range or chain out of bounds%s", "");
+    CK(cudaSetDevice(h->device));
+    return step_range(h, first, count, 1, chain, actions, obs, achieved, desired, reward, terminated, truncated, is_success,
+                      terminal_obs, terminal_achieved, (cudaStream_t)stream);
 }
 
 extern "C" int urgym_step(urgym_env_t *h, const float *actions, float *obs, float *achieved, float *desired,
@@ -297,7 +312,7 @@ extern "C" int urgym_step(urgym_env_t *h, const float *actions, float *obs, floa
     if (!actions || !obs || !reward || !terminated || !truncated || !is_success)
         return fail(h, URGYM_EINVAL, "urgym_step: actions, obs, reward, terminated, truncated, is_success must not be NULL%s", "");
     CK(cudaSetDevice(h->device));
-    return step_range(h, 0, h->n, 1, actions, obs, achieved, desired, reward, terminated, truncated, is_success,
+    return step_range(h, 0, h->n, 2, 0, actions, obs, achieved, desired, reward, terminated, truncated, is_success,
                       terminal_obs, terminal_achieved, (cudaStream_t)stream);
 }
 
@@ -427,7 +442,7 @@ extern "C" int urgym_step_host(urgym_env_t *h, const float *actions, float *obs,
         cudaStream_t s = h->cstream[k % 3];
         if (k < 3) { CK(cudaStreamWaitEvent(s, h->ev_fork, 0)); used = k + 1; }
         CK(cudaMemcpyAsync(d_act + first * 6, actions + first * 6, (size_t)cnt * 6 * 4, cudaMemcpyHostToDevice, s));
-        rc = step_range(h, first, cnt, 0, d_act, d_obs, achieved ? d_ach : nullptr, desired ? d_des : nullptr, d_rew, d_term,
+        rc = step_range(h, first, cnt, 0, 0, d_act, d_obs, achieved ? d_ach : nullptr, desired ? d_des : nullptr, d_rew, d_term,
                         d_trunc, d_succ, terminal_obs ? d_tobs : nullptr, terminal_achieved ? d_tach : nullptr, s);
         if (rc != URGYM_OK) return rc;
         CK(cudaMemcpyAsync(obs + first * D, d_obs + first * D, (size_t)cnt * D * 4, cudaMemcpyDeviceToHost, s));

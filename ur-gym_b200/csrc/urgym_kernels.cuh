@@ -25,6 +25,7 @@
 using namespace urgym;
 
 #define URGYM_BLOCK 128
+#define URGYM_MAX_CHAINS 4     /* independent step chains (env sub-ranges advanced on their own streams) */
 #ifndef URGYM_STEP_MINBLOCKS
 #define URGYM_STEP_MINBLOCKS 6      /* resident step-kernel blocks per SM the register allocation is held to */
 #endif
@@ -91,8 +92,9 @@ struct StepArgs {
     float *obs, *ach, *des, *rew;
     uint8_t *term, *trunc, *succ;
     unsigned long long *stats;
-    uint32_t *event;            // device-resident reset-event counter
-    int bump;                   // 1: this launch starts reset event number *event + 1 (0 when a step is split in ranges)
+    uint32_t *event;            // device-resident reset-event counters, one per chain (URGYM_MAX_CHAINS)
+    int bump;                   // 0: none (the caller bumped), 1: this chain's counter, 2: all counters (a whole step)
+    int chain;
     const float4 *hull;
 };
 
@@ -131,7 +133,10 @@ __global__ void __launch_bounds__(URGYM_BLOCK, URGYM_STEP_MINBLOCKS) urgym_step_
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < URGYM_STATS_COUNT) s_stats[tid] = 0ull;
-    if (A.bump && blockIdx.x == 0 && tid == 0) *A.event += 1u;    // this launch is reset event number *A.event
+    if (blockIdx.x == 0 && tid == 0) {                          // this launch is reset event number event[chain] + 1
+        if (A.bump == 1) A.event[A.chain] += 1u;
+        if (A.bump == 2) for (int c = 0; c < URGYM_MAX_CHAINS; c++) A.event[c] += 1u;
+    }
     const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
     __syncthreads();
 
@@ -222,6 +227,7 @@ struct AuxArgs {
     uint8_t *collision;
     unsigned long long *stats;
     const uint32_t *event;
+    int chain;
     const float4 *hull;
 };
 
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_c
     int *s_list = s_list_all + warp * URGYM_RESET_GROUP, *s_k = s_k_all + warp * URGYM_RESET_GROUP;
     const int64_t gbase = ((int64_t)blockIdx.x * NW + warp) * URGYM_RESET_GROUP;
     if (gbase >= A.n) return;
-    const uint32_t event = *A.event;
+    const uint32_t event = A.event[A.chain];
 
     // 1. compaction of the selected envs of this group: each lane reads the mask bytes of its GROUP/32 consecutive envs as
     //    32-bit words (the compiler merges them into one 16-byte load per mask array), a warp scan of the per-lane counts places the entries
@@ -403,7 +409,7 @@ template <int TASK, int GEOM> constexpr size_t reset_smem_bytes() {
            (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
 
-static __global__ void urgym_bump_kernel(uint32_t *event) { *event += 1u; }
+static __global__ void urgym_bump_kernel(uint32_t *event) { for (int c = 0; c < URGYM_MAX_CHAINS; c++) event[c] += 1u; }
 
 template <int TASK> __device__ __forceinline__ void write_rows(const AuxArgs &A, int64_t i, const float *row) {
     constexpr int D = Traits<TASK>::OBS, G = Traits<TASK>::GOAL;

@@ -107,18 +107,45 @@ class UR5VecEnv:
         """DummyVecEnv's info["TimeLimit.truncated"]: truncated and not terminated"""
         return self.truncated & (1 - self.terminated)
 
-    def capture_steps(self, action_buffers) -> "torch.cuda.CUDAGraph":
+    def capture_steps(self, action_buffers, chains: int = 1) -> "torch.cuda.CUDAGraph":
         """Capture one step per tensor of `action_buffers` (persistent device tensors the caller refills between
         replays) into a CUDA graph; graph.replay() then advances len(action_buffers) env steps with one launch from the
-        host.  The reset-event counter lives on the device, so replays draw fresh episodes."""
+        host.  The reset-event counters live on the device, so replays draw fresh episodes.
+
+        chains > 1 splits the envs into that many contiguous ranges, each advanced by its own branch of the graph
+        (urgym_step_range): the branches are independent, so one range's auto-reset kernel overlaps another range's
+        step kernel.  Results are identical to chains = 1."""
         for a in action_buffers:
             if a.device != self.device or a.dtype != torch.float32 or not a.is_contiguous() or a.shape != (self.num_envs, 6):
                 raise ValueError("capture_steps needs contiguous float32 [N,6] tensors on the simulator's device")
+        if not 1 <= chains <= 4:
+            raise ValueError("chains must be 1..4")
+        per = -(-self.num_envs // chains)
+        per = -(-per // 256) * 256                      # whole reset groups per chain
+        ranges = [(f, min(per, self.num_envs - f)) for f in range(0, self.num_envs, per)]
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            for a in action_buffers:
-                self.step(a)
+            main = torch.cuda.current_stream(self.device)
+            if len(ranges) == 1:
+                for a in action_buffers:
+                    self.step(a)
+            else:
+                side = [torch.cuda.Stream(self.device) for _ in ranges[1:]]
+                fork = torch.cuda.Event()
+                fork.record(main)
+                for c, (first, count) in enumerate(ranges):
+                    st = main if c == 0 else side[c - 1]
+                    if c:
+                        st.wait_event(fork)
+                    for a in action_buffers:
+                        rc = self.L.urgym_step_range(self.h, first, count, c, a.data_ptr(), *self._step_ptrs, st.cuda_stream)
+                        if rc != 0:
+                            nat.check(self.h, rc)
+                for st in side:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    main.wait_event(ev)
         return graph
 
     def reseed(self, seed: int) -> None:
