@@ -55,7 +55,7 @@ URGYM_HD void sincos_fast(float x, float *s, float *c) {
 // atan2 with 3e-7 absolute accuracy in ~25 instructions (libdevice's is ~55 and is called 8 times per env step):
 // reduce to t = min(|x|,|y|)/max(|x|,|y|) in [0,1], minimax odd polynomial for atan(t), undo the reductions.
 // The host instantiation uses libm.
-URGYM_HD float atan2_fast(float y, float x) {
+static URGYM_OOL float atan2_fast(float y, float x) {
 #ifdef __CUDA_ARCH__
     float ax = fabsf(x), ay = fabsf(y);
     float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
@@ -92,6 +92,13 @@ URGYM_HD float rsqrt_f(float x) {
     return rsqrtf(x);
 #else
     return 1.0f / sqrtf(x);
+#endif
+}
+URGYM_HD int __ffs_hd(unsigned x) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x);
+#else
+    return __builtin_ffs((int)x);
 #endif
 }
 URGYM_HD float fdiv(float a, float b) {               // division where 2 ulp are enough (clamped line parameters)
@@ -231,11 +238,20 @@ URGYM_HD Quat quat_from_mat(const float *R) {
 // a few 1e-7, and reading roll and yaw from different entries of such a matrix amplifies that defect by
 // 1/cos(pitch) near gimbal lock; a unit quaternion is an exact rotation, so the triple always encodes a rotation
 // within round-off of the true one.
-URGYM_HD float3 euler_from_mat(const float *R) {
+static URGYM_OOL float3 euler_via_quat_ool(const float *R) {     // near gimbal lock: rare, kept out of the hot instruction stream
     Quat q = quat_from_mat(R);
     float n = rsqrt_f(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
     q.x *= n; q.y *= n; q.z *= n; q.w *= n;
     return euler_from_quat(q);
+}
+URGYM_HD float3 euler_from_mat(const float *R) {
+    // For a unit quaternion the regular branch of getEulerFromQuaternion reads
+    //   -2(xz-wy) = -R20,  2(yz+wx) = R21,  w2-x2-y2+z2 = R22,  2(xy+wz) = R10,  w2+x2-y2-z2 = R00,
+    // so away from gimbal lock (amplification 1/cos(pitch) < 7) the triple comes straight from the matrix.
+    const float sarg = -R[6];
+    if (fabsf(sarg) < 0.99f)
+        return f3(atan2_fast(R[7], R[8]), atan2_fast(sarg, sqrtf(R[7] * R[7] + R[8] * R[8])), atan2_fast(R[3], R[0]));
+    return euler_via_quat_ool(R);
 }
 URGYM_HD void mat_from_quat(Quat q, float *R) {
     float n = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w, s = 2.0f / n;

@@ -121,7 +121,8 @@ URGYM_HD ObstW obstacle_dyn(const float *start, const float *vel, Quat qs, float
 // ------------------------------------------------------------------------------------------------ robot geometry
 // exact squared distance between segment ab and the axis-aligned box (c, he).  g(t) = 1/2 d/dt dist^2 is monotone
 // and piecewise linear with breakpoints where the point crosses a slab face; bracket the root between breakpoints.
-URGYM_HD float seg_box_dist2(float3 a, float3 b, float3 c, float3 he) {
+// (out of line: it runs only for links that come close to the table or the track)
+static URGYM_OOL float seg_box_dist2(float3 a, float3 b, float3 c, float3 he) {
     float3 p0 = a - c, d = b - a;
     auto ex = [](float p, float h) { return p - clampf(p, -h, h); };
     auto g = [&](float t) {
@@ -316,9 +317,18 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
                                  float *dist, float *cap, int cs) {
     Pose T;
     pose_identity(T);
+#ifdef URGYM_FK_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int l = 1; l < 7; l++) {
+#ifdef URGYM_FK_ROLLED
+        const float ql = l == 1 ? q[0] : (l == 2 ? q[1] : (l == 3 ? q[2] : (l == 4 ? q[3] : (l == 5 ? q[4] : q[5]))));
+        fk_advance(M, T, l - 1, ql);
+#else
         fk_advance(M, T, l - 1, q[l - 1]);
+#endif
         if (collide) {
             float3 a = T.p + rot(T.R, f3(M.cap_p0[l][0], M.cap_p0[l][1], M.cap_p0[l][2]));
             float3 b = T.p + rot(T.R, f3(M.cap_p1[l][0], M.cap_p1[l][1], M.cap_p1[l][2]));
@@ -342,10 +352,12 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
             hit = hit || (d <= URGYM_COLLISION_MARGIN);
             cap[(36 + l - 2) * cs] = d;
         }
-        // height broad phase: both boxes lie below z = box_top, most links stay well above it
-        if (fminf(a.z, b.z) - (URGYM_COLLISION_MARGIN + m + M.box_margin[0]) <= M.box_top) {
+        // height broad phase per box (table top z = -0.12, track top z = 0): most links stay well above both
+        const float zlow = fminf(a.z, b.z) - (URGYM_COLLISION_MARGIN + m + M.box_margin[0]);
+        if (zlow <= M.box_top) {
 #pragma unroll 1
             for (int box = 0; box < 2; box++) {
+                if (zlow > M.box_c[box][2] + M.box_he[box][2]) continue;
                 float margin = M.box_margin[box];
                 float reach = URGYM_COLLISION_MARGIN + m + margin;
                 float3 bc = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
@@ -355,19 +367,35 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
             }
         }
     }
-    // self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6)
-#pragma unroll 1
-    for (int p = 0; p < 9; p++) {
-        const int l1 = p < 4 ? 1 : (p < 7 ? 2 : 3);
-        const int l2 = p < 4 ? p + 3 : (p < 7 ? p : p - 2);
-        const float *c1 = cap + (l1 - 1) * 6 * cs, *c2 = cap + (l2 - 1) * 6 * cs;
-        const float3 a1 = f3(c1[0], c1[cs], c1[2 * cs]), b1 = f3(c1[3 * cs], c1[4 * cs], c1[5 * cs]);
-        const float3 a2 = f3(c2[0], c2[cs], c2[2 * cs]), b2 = f3(c2[3 * cs], c2[4 * cs], c2[5 * cs]);
-        const float reach = URGYM_COLLISION_MARGIN + M.fit_self[p];
-        const float3 dm = 0.5f * ((a1 + b1) - (a2 + b2));
-        const float far = reach + M.cap_hl[l1] + M.cap_hl[l2];
-        if (dot(dm, dm) <= far * far)       // sphere broad phase (exact bound)
+    // self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6).  Sphere broad phase for all nine with static indices (midpoints and
+    // half lengths), then the exact segment-segment test only for the pairs it leaves, in a rolled loop.
+    {
+        float3 mid[6];
+#pragma unroll
+        for (int l = 0; l < 6; l++) {
+            const float *c = cap + l * 6 * cs;
+            mid[l] = 0.5f * f3(c[0] + c[3 * cs], c[cs] + c[4 * cs], c[2 * cs] + c[5 * cs]);
+        }
+        unsigned need = 0u;
+#pragma unroll
+        for (int p = 0; p < 9; p++) {
+            const int l1 = p < 4 ? 1 : (p < 7 ? 2 : 3);
+            const int l2 = p < 4 ? p + 3 : (p < 7 ? p : p - 2);
+            const float3 dm = mid[l1 - 1] - mid[l2 - 1];
+            const float far = URGYM_COLLISION_MARGIN + M.fit_self[p] + M.cap_hl[l1] + M.cap_hl[l2];
+            if (dot(dm, dm) <= far * far) need |= 1u << p;
+        }
+        while (need) {
+            const int p = __ffs_hd(need) - 1;
+            need &= need - 1u;
+            const int l1 = p < 4 ? 1 : (p < 7 ? 2 : 3);
+            const int l2 = p < 4 ? p + 3 : (p < 7 ? p : p - 2);
+            const float *c1 = cap + (l1 - 1) * 6 * cs, *c2 = cap + (l2 - 1) * 6 * cs;
+            const float3 a1 = f3(c1[0], c1[cs], c1[2 * cs]), b1 = f3(c1[3 * cs], c1[4 * cs], c1[5 * cs]);
+            const float3 a2 = f3(c2[0], c2[cs], c2[2 * cs]), b2 = f3(c2[3 * cs], c2[4 * cs], c2[5 * cs]);
+            const float reach = URGYM_COLLISION_MARGIN + M.fit_self[p];
             hit = hit || (segseg_dist2_fast(a1, b1, a2, b2, M.cap_ia[l1], M.cap_ia[l2]) <= reach * reach);
+        }
     }
     if (Traits<TASK>::HAS_OBST) {
 #pragma unroll
