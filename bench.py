@@ -46,7 +46,7 @@ def workload_config(args, world):
     return {"workload": f"{args.task}, {args.envs_per_gpu} envs per GPU, random actions U(-1,1) resident in HBM, "
                         f"auto-reset on, {args.geometry} geometry",
             "task": args.task, "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
-            "geometry": args.geometry, "chains_per_gpu": args.chains, "sharding": f"env index ranges over {world} rank(s), no data-path collective",
+            "geometry": args.geometry, "chains_per_gpu": args.chains if args.envs_per_gpu >= (1 << 19) else 1, "sharding": f"env index ranges over {world} rank(s), no data-path collective",
             "l2": "per-step traffic (state + actions + outputs) exceeds the 126 MB L2; an 8-deep ring of action buffers"}
 
 
@@ -186,7 +186,8 @@ def run_ours(args, rank, world, local_rank):
     for k in range(warm):
         env.step(ring[k % 8])
     # the timed loop replays a CUDA graph of 8 steps (one per action buffer of the ring): 16 kernels per replay
-    graph = env.capture_steps(ring, chains=args.chains)
+    chains = args.chains if n >= (1 << 19) else 1       # small batches: sub-ranges would not fill the 148 SMs
+    graph = env.capture_steps(ring, chains=chains)
     graph.replay()
     env.stats(reset=True)
     steps = max(args.steps, 1)

@@ -305,3 +305,35 @@ def test_c_abi_error_behaviour(ug):
     assert b"must not be NULL" in L.urgym_last_error(h)
     assert L.urgym_get_state(h, 2, ctypes.c_void_p(1), None) == -5          # Ori has no obstacle
     assert L.urgym_destroy(h) == 0
+
+
+def test_sb3_style_vec_env_contract(ug):
+    """DummyVecEnv semantics train.py relies on: auto-reset, terminal_observation, TimeLimit.truncated, Monitor's
+    episode info, observation dict of numpy arrays"""
+    n = 512
+    venv = ug.SB3VecEnvAdapter("UR5DynReach-v1", n, seed=3)
+    ref = ug.UR5VecEnv("UR5DynReach-v1", n, seed=3)
+    obs = venv.reset(); ref.reset()
+    assert set(obs) == {"observation", "achieved_goal", "desired_goal"} and obs["observation"].shape == (n, 35)
+    assert obs["observation"].dtype == np.float32 and venv.action_space.shape == (6,)
+    rng = np.random.default_rng(0)
+    ret, length = np.zeros(n), np.zeros(n, int)
+    seen_done = seen_trunc = 0
+    for t in range(130):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        a[: n // 4] *= 0.02                                   # a quarter of the envs creep -> TimeLimit
+        obs, rew, dones, infos = venv.step(a)
+        o2, r2, te, tr, inf = ref.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(obs["observation"], o2["observation"].cpu().numpy())
+        assert np.array_equal(dones, (te | tr).bool().cpu().numpy()) and len(infos) == n
+        ret += rew; length += 1
+        for i in np.nonzero(dones)[0]:
+            info = infos[i]
+            assert np.array_equal(info["terminal_observation"]["observation"], inf["terminal_observation"][i].cpu().numpy())
+            assert abs(info["episode"]["r"] - ret[i]) < 1e-3 * max(1.0, abs(ret[i])) and info["episode"]["l"] == length[i]
+            assert info["TimeLimit.truncated"] == bool(tr[i].item() and not te[i].item())
+            seen_trunc += info["TimeLimit.truncated"]
+            ret[i] = 0; length[i] = 0; seen_done += 1
+        assert all("terminal_observation" not in infos[i] for i in np.nonzero(~dones)[0][:20])
+    assert seen_done > 0 and seen_trunc > 0
+    venv.close()

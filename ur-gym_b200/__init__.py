@@ -7,6 +7,7 @@
 from ._native import GEOM_CAPSULE, GEOM_HULL, LIB_PATH, STAT_NAMES, TASK_IDS, UrgymError  # noqa: F401
 from .envs import ENV_IDS, RobotTaskEnv, make, register_with_gymnasium  # noqa: F401
 from .sharding import allreduce_stats, shard_range, summarize  # noqa: F401
+from .sb3_vec_env import SB3VecEnvAdapter  # noqa: F401
 from .vec_env import UR5VecEnv  # noqa: F401
 
 register_with_gymnasium()
