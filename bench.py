@@ -211,6 +211,7 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
+    st = env.stats(reset=True)                        # episodes finished inside the timed region only
     clock_note = "sampled during the timed region (NVML, 5 ms period)"
     if len(sampler.samples) < 8:
         # the timed region was too short for the 5 ms sampler: keep sampling over an untimed repeat of the same loop
@@ -222,7 +223,7 @@ def run_ours(args, rank, world, local_rank):
     sampler.stop_flag = True
     launches = 2 * steps                              # step kernel + auto-reset kernel per env step
     barrier()
-    st = env.stats(reset=True)
+    env.stats(reset=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

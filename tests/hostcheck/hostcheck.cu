@@ -51,6 +51,7 @@ static void step_t(int64_t n, HcState S, const float *act, float *obs, float *re
     for (int64_t i = 0; i < n; i++) {
         EnvState s; StepOut o; float v[6] = {0, 0, 0, 0, 0, 0};
         get(S, i, s);
+        derive_cache<TASK>(s.E, s.C);       // what the reset / derive kernels leave in the hot planes
         float scratch[URGYM_SCRATCH_FLOATS];
         env_step<TASK, GEOM>(g_M, s, act + i * 6, g_hull.data(), obs + i * D, o, v, scratch, 1);
         put(S, i, s);
@@ -77,6 +78,7 @@ static void refresh_t(int64_t n, HcState S, uint8_t *coll) {
     for (int64_t i = 0; i < n; i++) {
         EnvState s;
         get(S, i, s);
+        derive_cache<TASK>(s.E, s.C);
         float scratch[URGYM_SCRATCH_FLOATS];
         coll[i] = env_refresh<TASK, GEOM>(g_M, s, g_hull.data(), scratch, 1);
         put(S, i, s);
@@ -88,6 +90,7 @@ static void observe_t(int64_t n, HcState S, const float *stale_vel, float *obs) 
     for (int64_t i = 0; i < n; i++) {
         EnvState s;
         get(S, i, s);
+        derive_cache<TASK>(s.E, s.C);
         env_observe<TASK, GEOM_CAPSULE>(g_M, s, stale_vel + i * 6, obs + i * D);
     }
 }

@@ -128,6 +128,7 @@ static const aux_launcher_t k_refresh[2][4] = {
     {urgym_inst_refresh_0_0, urgym_inst_refresh_1_0, urgym_inst_refresh_2_0, urgym_inst_refresh_3_0},
     {urgym_inst_refresh_0_1, urgym_inst_refresh_1_1, urgym_inst_refresh_2_1, urgym_inst_refresh_3_1}};
 static const aux_launcher_t k_observe[4] = {launch_observe<0>, launch_observe<1>, launch_observe<2>, launch_observe<3>};
+static const aux_launcher_t k_derive[4] = {launch_derive<0>, launch_derive<1>, launch_derive<2>, launch_derive<3>};
 
 static const aux_launcher_t k_prepare[2][4] = {
     {urgym_inst_prepare_0_0, urgym_inst_prepare_1_0, urgym_inst_prepare_2_0, urgym_inst_prepare_3_0},
@@ -165,7 +166,8 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
         // planes: 16-byte groups first, all 256-byte aligned
         const size_t n = (size_t)n_envs;
         const size_t p16 = align_up(n * 16, 256), p8 = align_up(n * 8, 256), p4 = align_up(n * 4, 256);
-        const size_t total = 3 * p16 + p4 + 4 * p16 + p8 + p4 + p16 + p8 + URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8 + 256;
+        const size_t total = 3 * p16 + p4 + 4 * p16 + p8 + p4 + p16 + p8 + 5 * p16 + p8 + p4 +
+                             URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8 + 256;
         if ((e = cudaMalloc(&h->pool, total)) != cudaSuccess) { rc = URGYM_ENOMEM; break; }
         if ((e = cudaMemset(h->pool, 0, total)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
         char *p = (char *)h->pool;
@@ -178,6 +180,9 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
         h->st.e1 = (float *)p; p += p4;
         h->st.va = (float4 *)p; p += p16;
         h->st.vb = (float2 *)p; p += p8;
+        for (int g = 0; g < 5; g++) { h->st.h4[g] = (float4 *)p; p += p16; }
+        h->st.h2 = (float2 *)p; p += p8;
+        h->st.h1 = (float *)p; p += p4;
         h->stats = (unsigned long long *)p; p += URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8;
         h->d_event = (uint32_t *)p;
         {
@@ -260,6 +265,8 @@ static StateView view_at(const StateView &v, int64_t off) {
     o.qa += off; o.qb += off; o.ld4 += off; o.ld1 += off;
     for (int g = 0; g < 4; g++) o.e4[g] += off;
     o.e2 += off; o.e1 += off; o.va += off; o.vb += off;
+    for (int g = 0; g < 5; g++) o.h4[g] += off;
+    o.h2 += off; o.h1 += off;
     return o;
 }
 
@@ -370,6 +377,14 @@ static int field_io(urgym_env *h, int field, void *ext, int to_state, void *stre
     urgym_field_kernel<<<grid_for(h->n), URGYM_BLOCK, 0, (cudaStream_t)stream>>>(A);
     CK(cudaGetLastError());
     h->launches++;
+    if (to_state && (field == URGYM_F_GOAL || field == URGYM_F_OBSTACLE || field == URGYM_F_OBSTACLE_END)) {
+        // the step reads the episode constants through the hot planes (with the episode cache): rebuild them
+        AuxArgs D;
+        memset(&D, 0, sizeof(D));
+        D.st = h->st; D.n = h->n;
+        CK(k_derive[h->task](h->model, D, (cudaStream_t)stream));
+        h->launches++;
+    }
     return URGYM_OK;
 }
 extern "C" int urgym_get_state(urgym_env_t *h, int field, void *dst, void *stream) { return field_io(h, field, dst, 0, stream); }

@@ -23,21 +23,28 @@ enum { GEOM_HULL = 0, GEOM_CAPSULE = 1 };
 #define URGYM_COLLISION_MARGIN 0.01f /* getClosestPoints(distance=0.01)  pyb_setup.py:401,410,421 */
 #define URGYM_DT_ENV 0.04f           /* 20 substeps x 1/500 s            pyb_setup.py:25,40,50 */
 
+// EH: leading words of E the step reads; CW: words of the episode cache C (derive_cache), quantities that depend on
+// the episode constants only and are therefore computed once per episode, at reset, instead of once per step:
+//   Ori  C = goal quaternion[4]                                  (utils.py:48-54 applied to the goal)
+//   Obs  C = obstacle axis[3]
+//   Sta  C = goal quaternion[4], obstacle axis[3], obstacle Euler read-back[3]   (reach.py:455-457)
+//   Dyn  C = goal quaternion[4], start quaternion[4], ReachDyn.velocity[6]       (reach.py:728-753)
+// The step kernel reads the "hot" words H = E[0..EH) ++ C[0..CW) from their own planes.
 template <int TASK> struct Traits;
 template <> struct Traits<TASK_ORI> {
-    static constexpr int OBS = 18, GOAL = 6, EW = 6, BPI = 2, OBST = -1;
+    static constexpr int OBS = 18, GOAL = 6, EW = 6, BPI = 2, OBST = -1, EH = 6, CW = 4;
     static constexpr bool HAS_OBST = false, ORI = true, DYN = false;
 };
 template <> struct Traits<TASK_OBS> {
-    static constexpr int OBS = 26, GOAL = 3, EW = 9, BPI = 3, OBST = 3;
+    static constexpr int OBS = 26, GOAL = 3, EW = 9, BPI = 3, OBST = 3, EH = 9, CW = 3;
     static constexpr bool HAS_OBST = true, ORI = false, DYN = false;
 };
 template <> struct Traits<TASK_STA> {
-    static constexpr int OBS = 29, GOAL = 6, EW = 12, BPI = 3, OBST = 6;
+    static constexpr int OBS = 29, GOAL = 6, EW = 12, BPI = 3, OBST = 6, EH = 9, CW = 10;
     static constexpr bool HAS_OBST = true, ORI = true, DYN = false;
 };
 template <> struct Traits<TASK_DYN> {
-    static constexpr int OBS = 35, GOAL = 6, EW = 18, BPI = 5, OBST = 6;   // OBST = obstacle_start; end = OBST + 6
+    static constexpr int OBS = 35, GOAL = 6, EW = 18, BPI = 5, OBST = 6, EH = 9, CW = 14;   // OBST = obstacle_start; end = OBST + 6
     static constexpr bool HAS_OBST = true, ORI = true, DYN = true;
 };
 
@@ -58,6 +65,7 @@ struct EnvState {
     float ep_ret;
     float ld[5];
     float E[18];
+    float C[14];        // episode cache (derive_cache)
 };
 
 struct StepOut {
@@ -71,6 +79,11 @@ struct ObstW {          // obstacle in the world: centre, orientation, unit axis
     Quat q;
     float3 u;
 };
+URGYM_HD ObstW obstacle_none() {
+    ObstW O;
+    O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
+    return O;
+}
 URGYM_HD float3 quat_axis_z(Quat q) {     // third column of the rotation matrix of a unit quaternion
     return f3(2.0f * (q.x * q.z + q.w * q.y), 2.0f * (q.y * q.z - q.w * q.x), 1.0f - 2.0f * (q.x * q.x + q.y * q.y));
 }
@@ -106,15 +119,55 @@ URGYM_HD void dyn_twist(const float *start, const float *end, float *vel, Quat &
     vel[0] = (end[0] - start[0]) * 0.5f; vel[1] = (end[1] - start[1]) * 0.5f; vel[2] = (end[2] - start[2]) * 0.5f;
     vel[3] = axis.x * angle * 0.5f; vel[4] = axis.y * angle * 0.5f; vel[5] = axis.z * angle * 0.5f;
 }
-URGYM_HD ObstW obstacle_dyn(const float *start, const float *vel, Quat qs, float3 axis, float angle, int moved) {
-    ObstW O;
-    float t = (float)moved * URGYM_DT_ENV;
-    O.c = f3(start[0] + t * vel[0], start[1] + t * vel[1], start[2] + t * vel[2]);
-    float s, c;
-    sincos_fast(0.25f * t * angle, &s, &c);          // half of the rotated angle t * (angle / 2)
-    Quat r; r.x = axis.x * s; r.y = axis.y * s; r.z = axis.z * s; r.w = c;
-    O.q = quat_mul(r, qs);                        // world-frame increment on the left
-    O.u = quat_axis_z(O.q);
+// episode cache: everything the step needs that depends on the episode constants E only (see Traits)
+template <int TASK> URGYM_HD void derive_cache(const float *E, float *C) {
+    typedef Traits<TASK> TT;
+    if (TT::ORI) {                      // angular_distance's quaternion of the goal          utils.py:48-54
+        Quat g = quat_ZYX(E[3], E[4], E[5]);
+        C[0] = g.x; C[1] = g.y; C[2] = g.z; C[3] = g.w;
+    }
+    if (TASK == TASK_OBS) {
+        ObstW O = obstacle_static(&E[3]);
+        C[0] = O.u.x; C[1] = O.u.y; C[2] = O.u.z;
+    } else if (TASK == TASK_STA) {      // static obstacle: axis and the pose read-back of get_obs   reach.py:455-457
+        ObstW O = obstacle_static(&E[6]);
+        float3 e = euler_from_quat(O.q);
+        C[4] = O.u.x; C[5] = O.u.y; C[6] = O.u.z; C[7] = e.x; C[8] = e.y; C[9] = e.z;
+    } else if (TASK == TASK_DYN) {      // ReachDyn.set_velocity's twist is the same at every step of an episode
+        Quat qs; float3 axis; float angle; float tw[6];
+        dyn_twist(&E[6], &E[12], tw, qs, axis, angle);
+        C[4] = qs.x; C[5] = qs.y; C[6] = qs.z; C[7] = qs.w;
+#pragma unroll
+        for (int k = 0; k < 6; k++) C[8 + k] = tw[k];
+    }
+}
+// obstacle pose after `moved` env steps of motion and its Euler read-back (get_base_rotation), from E[0..EH) and C.
+// Dyn: translation moved*0.04*v, rotation by moved*0.04*|w| about w = axis*angle/2 (Bullet composes one fixed
+// world-frame increment per substep), so the half angle is 0.5*t*|w| and sin(half)*axis = w * sin(half)/|w|.
+template <int TASK> URGYM_HD ObstW obstacle_cached(const float *E, const float *C, int moved, float3 &euler) {
+    ObstW O = obstacle_none();
+    euler = f3(0, 0, 0);
+    if (TASK == TASK_OBS) {
+        O.c = f3(E[3], E[4], E[5]); O.u = f3(C[0], C[1], C[2]);
+        euler = f3(E[6], E[7], E[8]);                   // Obs shows the Euler triple as sampled (quirk Q3)
+    } else if (TASK == TASK_STA) {
+        O.c = f3(E[6], E[7], E[8]); O.u = f3(C[4], C[5], C[6]);
+        euler = f3(C[7], C[8], C[9]);
+    } else if (TASK == TASK_DYN) {
+        const float t = (float)moved * URGYM_DT_ENV;
+        O.c = f3(fmaf(t, C[8], E[6]), fmaf(t, C[9], E[7]), fmaf(t, C[10], E[8]));
+        const float3 w = f3(C[11], C[12], C[13]);
+        const float wn2 = dot(w, w);
+        const float inv = wn2 > 0.0f ? rsqrt_f(wn2) : 0.0f;
+        float sn, cs;
+        sincos_fast(0.5f * t * (wn2 * inv), &sn, &cs);
+        const float k = sn * inv;
+        Quat r; r.x = w.x * k; r.y = w.y * k; r.z = w.z * k; r.w = cs;
+        Quat qs; qs.x = C[4]; qs.y = C[5]; qs.z = C[6]; qs.w = C[7];
+        O.q = quat_mul(r, qs);                          // world-frame increment on the left
+        O.u = quat_axis_z(O.q);
+        euler = euler_from_quat(O.q);
+    }
     return O;
 }
 
@@ -415,7 +468,7 @@ URGYM_HD bool robot_pass(const ModelConst &M, const float *q, const float *qrow,
 // task part of the observation   reach.py:189-190 (Ori), 307-308 (Obs), 454-458 (Sta), 653-657 (Dyn)
 // row[0..11] = robot obs (ee pos, ee euler, q).  vel == nullptr keeps the velocity columns as they are (stale, quirk Q4).
 template <int TASK>
-URGYM_HD void write_obs_row(float *row, const float *ee, const float *q, const float *E, const ObstW &O,
+URGYM_HD void write_obs_row(float *row, const float *ee, const float *q, const float *E, const ObstW &O, float3 e,
                             const float *vel, const float *ld) {
     typedef Traits<TASK> TT;
 #pragma unroll
@@ -427,8 +480,7 @@ URGYM_HD void write_obs_row(float *row, const float *ee, const float *q, const f
         for (int k = 0; k < 6; k++) row[15 + k] = E[3 + k];
 #pragma unroll
         for (int k = 0; k < 5; k++) row[21 + k] = ld[k];
-    } else if (TASK == TASK_STA || TASK == TASK_DYN) {   // obstacle pose read back: position + getEulerFromQuaternion
-        float3 e = euler_from_quat(O.q);
+    } else if (TASK == TASK_STA || TASK == TASK_DYN) {   // obstacle pose read back: position + getEulerFromQuaternion (e)
         row[18] = O.c.x; row[19] = O.c.y; row[20] = O.c.z; row[21] = e.x; row[22] = e.y; row[23] = e.z;
         if (TASK == TASK_DYN) {
             if (vel) {
@@ -446,13 +498,14 @@ URGYM_HD void write_obs_row(float *row, const float *ee, const float *q, const f
 
 // success test + the two goal distances   reach.py:212-215,348-350,543-546,755-758; utils.py:5-69
 template <int TASK>
-URGYM_HD bool goal_metrics(const float *ee, const float *E, float &d, float &ang) {
+URGYM_HD bool goal_metrics(const float *ee, const float *E, const float *C, float &d, float &ang) {
     float dx = ee[0] - E[0], dy = ee[1] - E[1], dz = ee[2] - E[2];
     d = sqrtf(dx * dx + dy * dy + dz * dz);
     bool ok = d < 0.05f;
     ang = 0.0f;
     if (Traits<TASK>::ORI) {
-        ang = angular_distance(quat_ZYX(ee[3], ee[4], ee[5]), quat_ZYX(E[3], E[4], E[5]));
+        Quat g; g.x = C[0]; g.y = C[1]; g.z = C[2]; g.w = C[3];
+        ang = angular_distance(quat_ZYX(ee[3], ee[4], ee[5]), g);
         ok = ok && (ang < 0.0873f);
     }
     return ok;
@@ -468,25 +521,17 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
     // 1. UR5Ori.set_action: clip, * pi, * 0.1 (float32 like the numpy expression), teleport      UR5.py:273-279,314-317
 #pragma unroll
     for (int j = 0; j < 6; j++) s.q[j] += (clampf(act[j], -1.0f, 1.0f) * URGYM_PI_F) * 0.1f;
-    URGYM_WARP_SYNC();      // `scratch` may overlay the action / observation tile: every lane has read its action
-    // 2. task.set_velocity + sim.step: obstacle pose after this step                           core.py:305-309
-    ObstW O;
+    // 2. task.set_velocity + sim.step: obstacle pose after this step (twist from the episode cache)   core.py:305-309
+    float3 oe;
     float vel[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    const ObstW O = obstacle_cached<TASK>(s.E, s.C, s.elapsed + 1 < 25 ? s.elapsed + 1 : 25, oe);
     if (TT::DYN) {
-        Quat qs; float3 axis; float angle; float tw[6];
-        dyn_twist(&s.E[6], &s.E[12], tw, qs, axis, angle);
-        int moved = s.elapsed + 1 < 25 ? s.elapsed + 1 : 25;
-        O = obstacle_dyn(&s.E[6], tw, qs, axis, angle, moved);
-        if (s.elapsed < 25) {
+        if (s.elapsed < 25) {           // ReachDyn.velocity: the twist while step_num < 25, zeros afterwards
 #pragma unroll
-            for (int k = 0; k < 6; k++) vel[k] = tw[k];
+            for (int k = 0; k < 6; k++) vel[k] = s.C[8 + k];
         }
 #pragma unroll
         for (int k = 0; k < 6; k++) vel_out[k] = vel[k];
-    } else if (TT::HAS_OBST) {
-        O = obstacle_static(&s.E[TT::OBST]);
-    } else {
-        O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
     }
     // 3. FK and collision                                                                      core.py:310
     float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -497,10 +542,10 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
     bool coll = robot_pass<TASK, GEOM>(M, s.q, row + 6, O, hv, true, ee, dist, scratch, cs);
     URGYM_WARP_SYNC();      // every lane is done with the scratch before observation rows are written over it
     // 4. observation: carries link_dist from BEFORE this step's reward (quirk Q1)               core.py:311
-    write_obs_row<TASK>(row, ee, s.q, s.E, O, vel, s.ld);
+    write_obs_row<TASK>(row, ee, s.q, s.E, O, oe, vel, s.ld);
     // 5. termination                                                                           core.py:313-315
     float d, ang;
-    bool succ = goal_metrics<TASK>(ee, s.E, d, ang);
+    bool succ = goal_metrics<TASK>(ee, s.E, s.C, d, ang);
     o.collision = coll;
     o.terminated = succ || coll;
     o.success = o.terminated && !coll;
@@ -545,24 +590,18 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
 template <int TASK, int GEOM>
 URGYM_HD void env_observe(const ModelConst &M, const EnvState &s, const float *stale_vel, float *row) {
     typedef Traits<TASK> TT;
-    ObstW O;
+    float3 oe;
     float vel[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    const ObstW O = obstacle_cached<TASK>(s.E, s.C, s.elapsed < 25 ? s.elapsed : 25, oe);
     if (TT::DYN) {
-        Quat qs; float3 axis; float angle; float tw[6];
-        dyn_twist(&s.E[6], &s.E[12], tw, qs, axis, angle);
-        O = obstacle_dyn(&s.E[6], tw, qs, axis, angle, s.elapsed < 25 ? s.elapsed : 25);
 #pragma unroll
-        for (int k = 0; k < 6; k++) vel[k] = s.elapsed == 0 ? stale_vel[k] : (s.elapsed <= 25 ? tw[k] : 0.0f);
-    } else if (TT::HAS_OBST) {
-        O = obstacle_static(&s.E[TT::OBST]);
-    } else {
-        O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
+        for (int k = 0; k < 6; k++) vel[k] = s.elapsed == 0 ? stale_vel[k] : (s.elapsed <= 25 ? s.C[8 + k] : 0.0f);
     }
     float ee[6], du[5];
 #pragma unroll
     for (int k = 0; k < 6; k++) row[6 + k] = s.q[k];
     robot_pass<TASK, GEOM_CAPSULE>(M, s.q, row + 6, O, nullptr, false, ee, du, nullptr, 1);   // EE pose only
-    write_obs_row<TASK>(row, ee, s.q, s.E, O, vel, s.ld);
+    write_obs_row<TASK>(row, ee, s.q, s.E, O, oe, vel, s.ld);
 }
 
 // tail of set_goal_and_obstacle / reset: collision flag and link_dist = last_dist at the current state
@@ -570,16 +609,8 @@ URGYM_HD void env_observe(const ModelConst &M, const EnvState &s, const float *s
 template <int TASK, int GEOM>
 URGYM_HD bool env_refresh(const ModelConst &M, EnvState &s, const float4 *hv, float *scratch, int cs) {
     typedef Traits<TASK> TT;
-    ObstW O;
-    if (TT::DYN) {
-        Quat qs; float3 axis; float angle; float tw[6];
-        dyn_twist(&s.E[6], &s.E[12], tw, qs, axis, angle);
-        O = obstacle_dyn(&s.E[6], tw, qs, axis, angle, s.elapsed < 25 ? s.elapsed : 25);
-    } else if (TT::HAS_OBST) {
-        O = obstacle_static(&s.E[TT::OBST]);
-    } else {
-        O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
-    }
+    float3 oe;
+    const ObstW O = obstacle_cached<TASK>(s.E, s.C, s.elapsed < 25 ? s.elapsed : 25, oe);
     float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     bool coll = robot_pass<TASK, GEOM>(M, s.q, s.q, O, hv, true, ee, dist, scratch, cs);
     if (TT::HAS_OBST) {
@@ -681,13 +712,14 @@ template <int TASK, int GEOM>
 URGYM_HD int env_reset(const ModelConst &M, EnvState &s, ResetStream rs, const float4 *hv, float *row, int k_start = 0) {
     typedef Traits<TASK> TT;
     int iters = sample_episode<TASK, GEOM>(M, rs, s.E, k_start);
+    derive_cache<TASK>(s.E, s.C);
 #pragma unroll
     for (int j = 0; j < 6; j++) s.q[j] = M.neutral_q[j];
     s.elapsed = 0;
     s.ep_ret = 0.0f;
-    ObstW O;
+    float3 oe;
+    const ObstW O = obstacle_cached<TASK>(s.E, s.C, 0, oe);     // Dyn: obstacle placed at START after sampling   reach.py:678
     if (TT::HAS_OBST) {
-        O = obstacle_static(&s.E[TT::OBST]);           // Dyn: obstacle placed at START after sampling   reach.py:678
 #pragma unroll 1
         for (int l = 2; l < 7; l++) {                   // reach.py:323-324,478-479,680-681
             LinkShape<GEOM> L;
@@ -696,11 +728,10 @@ URGYM_HD int env_reset(const ModelConst &M, EnvState &s, ResetStream rs, const f
             if (l == 2) s.ld[0] = d; else if (l == 3) s.ld[1] = d; else if (l == 4) s.ld[2] = d; else if (l == 5) s.ld[3] = d; else s.ld[4] = d;
         }
     } else {
-        O.c = f3(0, 0, 0); O.q.x = O.q.y = O.q.z = 0.0f; O.q.w = 1.0f; O.u = f3(0, 0, 1);
 #pragma unroll
         for (int k = 0; k < 5; k++) s.ld[k] = 0.0f;
     }
-    write_obs_row<TASK>(row, M.neutral_ee, s.q, s.E, O, nullptr, s.ld);
+    write_obs_row<TASK>(row, M.neutral_ee, s.q, s.E, O, oe, nullptr, s.ld);
     return iters;
 }
 

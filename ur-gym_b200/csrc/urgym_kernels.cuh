@@ -44,6 +44,11 @@ struct StateView {
     float *e1;
     float4 *va;
     float2 *vb;
+    // hot planes: the words of E the step reads plus the episode cache C (urgym_env.cuh, Traits::EH / CW), written at
+    // reset (and after a state injection), read by every step instead of e4/e2/e1
+    float4 *h4[5];
+    float2 *h2;
+    float *h1;
 };
 
 template <int TASK> __device__ __forceinline__ void load_E(const StateView &st, int64_t i, float *E) {
@@ -62,6 +67,34 @@ template <int TASK> __device__ __forceinline__ void store_E(const StateView &st,
     for (int g = 0; g < NF; g++) st.e4[g][i] = make_float4(E[4 * g], E[4 * g + 1], E[4 * g + 2], E[4 * g + 3]);
     if (TAIL == 2) st.e2[i] = make_float2(E[4 * NF], E[4 * NF + 1]);
     if (TAIL == 1) st.e1[i] = E[4 * NF];
+}
+// hot words H = E[0..EH) ++ C[0..CW): HW/4 float4 planes, then a float2 and/or a float plane for the tail
+template <int TASK> struct HotLayout {
+    static constexpr int EH = Traits<TASK>::EH, CW = Traits<TASK>::CW, HW = EH + CW, NF = HW / 4, TAIL = HW % 4;
+    static_assert(NF <= 5, "hot planes");
+};
+template <int TASK> __device__ __forceinline__ float &hot_word(EnvState &s, int w) {
+    return w < HotLayout<TASK>::EH ? s.E[w] : s.C[w - HotLayout<TASK>::EH];
+}
+template <int TASK> __device__ __forceinline__ void load_hot(const StateView &st, int64_t i, EnvState &s) {
+    typedef HotLayout<TASK> L;
+#pragma unroll
+    for (int g = 0; g < L::NF; g++) {
+        const float4 v = st.h4[g][i];
+        hot_word<TASK>(s, 4 * g) = v.x; hot_word<TASK>(s, 4 * g + 1) = v.y; hot_word<TASK>(s, 4 * g + 2) = v.z; hot_word<TASK>(s, 4 * g + 3) = v.w;
+    }
+    if (L::TAIL >= 2) { const float2 v = st.h2[i]; hot_word<TASK>(s, 4 * L::NF) = v.x; hot_word<TASK>(s, 4 * L::NF + 1) = v.y; }
+    if (L::TAIL == 1) hot_word<TASK>(s, 4 * L::NF) = st.h1[i];
+    if (L::TAIL == 3) hot_word<TASK>(s, 4 * L::NF + 2) = st.h1[i];
+}
+template <int TASK> __device__ __forceinline__ void store_hot(const StateView &st, int64_t i, EnvState &s) {
+    typedef HotLayout<TASK> L;
+#pragma unroll
+    for (int g = 0; g < L::NF; g++)
+        st.h4[g][i] = make_float4(hot_word<TASK>(s, 4 * g), hot_word<TASK>(s, 4 * g + 1), hot_word<TASK>(s, 4 * g + 2), hot_word<TASK>(s, 4 * g + 3));
+    if (L::TAIL >= 2) st.h2[i] = make_float2(hot_word<TASK>(s, 4 * L::NF), hot_word<TASK>(s, 4 * L::NF + 1));
+    if (L::TAIL == 1) st.h1[i] = hot_word<TASK>(s, 4 * L::NF);
+    if (L::TAIL == 3) st.h1[i] = hot_word<TASK>(s, 4 * L::NF + 2);
 }
 template <int TASK> __device__ __forceinline__ void load_dyn(const StateView &st, int64_t i, EnvState &s) {
     float4 a = st.qa[i], b = st.qb[i];
@@ -107,18 +140,19 @@ template <int GEOM> __device__ __forceinline__ const float4 *stage_hull(const fl
     for (int i = threadIdx.x; i < UR5E_NUM_HULL_VERTS; i += blockDim.x) s[i] = g[i];
     return s;
 }
-// per-warp tile: 32 observation rows, 32 action rows; the capsule pass's scratch column block [41][32] overlays it
+// per-warp tile: 32 observation rows; the capsule pass's scratch column block [41][32] overlays it
 template <int TASK> struct TileFloats {
-    static constexpr int value = (Traits<TASK>::OBS + 6) > URGYM_SCRATCH_FLOATS ? (Traits<TASK>::OBS + 6) : URGYM_SCRATCH_FLOATS;
+    static constexpr int value = Traits<TASK>::OBS > URGYM_SCRATCH_FLOATS ? Traits<TASK>::OBS : URGYM_SCRATCH_FLOATS;
 };
 template <int TASK, int GEOM> constexpr size_t step_smem_bytes() {
     return (size_t)URGYM_BLOCK * TileFloats<TASK>::value * sizeof(float) +
            (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
+__device__ __forceinline__ void stat_add(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }   // RED.E.ADD.64 (result unused)
 
 // ------------------------------------------------------------------------------------------------ step
-// One env per thread; every warp owns a private 32-row tile of the action and observation arrays in shared memory,
-// so apart from the hull staging (hull mode) and the block's statistics there is no block-wide synchronisation.
+// One env per thread; every warp owns a private 32-row tile of the observation array in shared memory and there is
+// no block-wide synchronisation (apart from the hull staging in hull mode): warps start, run and retire on their own.
 // Finished envs are NOT reset here: the step only raises their terminated / truncated flags, and the auto-reset
 // kernel that follows in the stream handles them in dense form.
 template <int TASK, int GEOM>
@@ -127,92 +161,86 @@ __global__ void __launch_bounds__(URGYM_BLOCK, URGYM_STEP_MINBLOCKS) urgym_step_
     constexpr int D = TT::OBS, G = TT::GOAL, B = URGYM_BLOCK, W = 32;
     constexpr int TF = TileFloats<TASK>::value;
     extern __shared__ float4 smem4[];
-    float *s_tiles = reinterpret_cast<float *>(smem4);        // [warps][32 * TF]: obs tile [32][D], then action tile [32][6]
+    float *s_tiles = reinterpret_cast<float *>(smem4);        // [warps][32 * TF]: obs tile [32][D]
     float4 *s_hull = reinterpret_cast<float4 *>(s_tiles + B * TF);
-    __shared__ unsigned long long s_stats[URGYM_STATS_COUNT];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < URGYM_STATS_COUNT) s_stats[tid] = 0ull;
     if (blockIdx.x == 0 && tid == 0) {                          // this launch is reset event number event[chain] + 1
         if (A.bump == 1) A.event[A.chain] += 1u;
         if (A.bump == 2) for (int c = 0; c < URGYM_MAX_CHAINS; c++) A.event[c] += 1u;
     }
     const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
-    __syncthreads();
+    if (GEOM == GEOM_HULL) __syncthreads();
 
     const int64_t wbase = (int64_t)blockIdx.x * B + warp * W;                 // first env of this warp
-    const int rows = (A.n - wbase) < W ? (int)max((long long)(A.n - wbase), 0ll) : W;
-    float *s_obs = s_tiles + warp * W * TF, *s_act = s_obs + W * D;
+    if (wbase >= A.n) return;
+    const int rows = (A.n - wbase) < W ? (int)(A.n - wbase) : W;
+    float *s_obs = s_tiles + warp * W * TF;
     float *s_scr = s_obs + lane;                              // capsule scratch: column `lane` of a [41][32] block
 
-    // action tile: 16-byte vectorised, coalesced
-    if (rows > 0) {
-        const float *gact = A.actions + wbase * 6;
-        if (rows == W && aligned16(gact)) {
-            const float4 *g4 = reinterpret_cast<const float4 *>(gact);
-            float4 *s4 = reinterpret_cast<float4 *>(s_act);
-            for (int k = lane; k < W * 6 / 4; k += W) s4[k] = __ldcs(g4 + k);
+    // every lane runs the step (warp-level barriers inside); lanes past the end redo the last env and store nothing
+    const bool live = lane < rows;
+    const int64_t i = wbase + (live ? lane : rows - 1);
+    EnvState s;
+    StepOut o;
+    float vel[6], act[6];
+    {   // the lane's own action row: 24 contiguous bytes (the warp's three requests cover the same 768 bytes)
+        const float *ga = A.actions + i * 6;
+        if ((reinterpret_cast<uintptr_t>(A.actions) & 7u) == 0) {
+            const float2 a0 = __ldg(reinterpret_cast<const float2 *>(ga)), a1 = __ldg(reinterpret_cast<const float2 *>(ga) + 1),
+                         a2 = __ldg(reinterpret_cast<const float2 *>(ga) + 2);
+            act[0] = a0.x; act[1] = a0.y; act[2] = a1.x; act[3] = a1.y; act[4] = a2.x; act[5] = a2.y;
         } else {
-            for (int k = lane; k < rows * 6; k += W) s_act[k] = gact[k];
+#pragma unroll
+            for (int k = 0; k < 6; k++) act[k] = __ldg(ga + k);
         }
     }
-    __syncwarp();
-
-    if (rows > 0) {
-        // every lane runs the step (warp-level barriers inside); lanes past the end redo the last env and store nothing
-        const bool live = lane < rows;
-        const int64_t i = wbase + (live ? lane : rows - 1);
-        EnvState s;
-        StepOut o;
-        float vel[6];
-        load_dyn<TASK>(A.st, i, s);
-        load_E<TASK>(A.st, i, s.E);
-        env_step<TASK, GEOM>(c_model, s, s_act + (live ? lane : rows - 1) * 6, hv, s_obs + lane * D, o, vel, s_scr, W);
-        if (live) {
-            store_dyn<TASK>(A.st, i, s);
-            A.rew[i] = o.reward;
-            A.term[i] = o.terminated ? 1 : 0;
-            A.trunc[i] = o.truncated ? 1 : 0;
-            A.succ[i] = o.success ? 1 : 0;
-            if (o.terminated || o.truncated) {
-                atomicAdd(&s_stats[0], 1ull);
-                atomicAdd(&s_stats[1], (unsigned long long)__float2ll_rn(s.ep_ret * URGYM_RETURN_SCALE));
-                atomicAdd(&s_stats[2], (unsigned long long)s.elapsed);
-                if (o.success) atomicAdd(&s_stats[3], 1ull);
-                if (o.collision) atomicAdd(&s_stats[4], 1ull);
-                if (o.truncated && !o.terminated) atomicAdd(&s_stats[5], 1ull);
-            }
+    load_dyn<TASK>(A.st, i, s);
+    load_hot<TASK>(A.st, i, s);
+    env_step<TASK, GEOM>(c_model, s, act, hv, s_obs + lane * D, o, vel, s_scr, W);
+    if (live) {
+        store_dyn<TASK>(A.st, i, s);
+        A.rew[i] = o.reward;
+        A.term[i] = o.terminated ? 1 : 0;
+        A.trunc[i] = o.truncated ? 1 : 0;
+        A.succ[i] = o.success ? 1 : 0;
+        // episode statistics: a few finished envs per warp, each adds its own figures (no result is read back)
+        unsigned long long *slot = A.stats + (size_t)((blockIdx.x * (B / W) + warp) % URGYM_STAT_SLOTS) * URGYM_STATS_COUNT;
+        if (o.terminated || o.truncated) {
+            stat_add(slot + 0, 1ull);
+            stat_add(slot + 1, (unsigned long long)__float2ll_rn(s.ep_ret * URGYM_RETURN_SCALE));
+            stat_add(slot + 2, (unsigned long long)s.elapsed);
+            if (o.success) stat_add(slot + 3, 1ull);
+            if (o.collision) stat_add(slot + 4, 1ull);
+            if (o.truncated && !o.terminated) stat_add(slot + 5, 1ull);
         }
+        if (lane == 0) stat_add(slot + 6, (unsigned long long)rows);
     }
     __syncwarp();
     // observation tile -> global, 16-byte vectorised
-    if (rows > 0) {
-        float *gobs = A.obs + wbase * D;
-        if (rows == W && aligned16(gobs)) {
-            float4 *g4 = reinterpret_cast<float4 *>(gobs);
-            const float4 *s4 = reinterpret_cast<const float4 *>(s_obs);
-            for (int k = lane; k < W * D / 4; k += W) __stcs(g4 + k, s4[k]);
-        } else {
-            for (int k = lane; k < rows * D; k += W) gobs[k] = s_obs[k];
-        }
-        if (lane < rows) {  // achieved_goal = first G observation columns, desired_goal = columns 12..12+G of the own row
-            const float *row = s_obs + lane * D;
-            if (A.ach) {
-                float *g = A.ach + (wbase + lane) * G;
+    float *gobs = A.obs + wbase * D;
+    if (rows == W && aligned16(gobs)) {
+        float4 *g4 = reinterpret_cast<float4 *>(gobs);
+        const float4 *s4 = reinterpret_cast<const float4 *>(s_obs);
 #pragma unroll
-                for (int k = 0; k < G; k++) g[k] = row[k];
-            }
-            if (A.des) {
-                float *g = A.des + (wbase + lane) * G;
-#pragma unroll
-                for (int k = 0; k < G; k++) g[k] = row[12 + k];
-            }
-        }
-        if (lane == 0) atomicAdd(&s_stats[6], (unsigned long long)rows);
+        for (int k = 0; k < (W * D / 4 + W - 1) / W; k++)
+            if (k * W + lane < W * D / 4) __stcs(g4 + k * W + lane, s4[k * W + lane]);
+    } else {
+        for (int k = lane; k < rows * D; k += W) gobs[k] = s_obs[k];
     }
-    __syncthreads();
-    if (tid < URGYM_STATS_COUNT && s_stats[tid] != 0ull)
-        atomicAdd(&A.stats[(blockIdx.x % URGYM_STAT_SLOTS) * URGYM_STATS_COUNT + tid], s_stats[tid]);
+    if (live) {  // achieved_goal = first G observation columns, desired_goal = columns 12..12+G of the own row
+        const float *row = s_obs + lane * D;
+        if (A.ach) {
+            float *g = A.ach + (wbase + lane) * G;
+#pragma unroll
+            for (int k = 0; k < G; k++) g[k] = row[k];
+        }
+        if (A.des) {
+            float *g = A.des + (wbase + lane) * G;
+#pragma unroll
+            for (int k = 0; k < G; k++) g[k] = row[12 + k];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ reset / auto-reset
@@ -362,15 +390,13 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_c
                     for (int k = 0; k < 6; k++) vel[k] = A.obs[i * D + 24 + k];
                 } else {
                     load_dyn<TASK>(A.st, i, s);
-                    load_E<TASK>(A.st, i, s.E);
+                    load_hot<TASK>(A.st, i, s);
                     if (s.elapsed == 0) {
                         float4 a = A.st.va[i]; float2 b = A.st.vb[i];
                         vel[0] = a.x; vel[1] = a.y; vel[2] = a.z; vel[3] = a.w; vel[4] = b.x; vel[5] = b.y;
                     } else {
-                        Quat qs; float3 axis; float angle; float tw[6];
-                        dyn_twist(&s.E[6], &s.E[12], tw, qs, axis, angle);
 #pragma unroll
-                        for (int k = 0; k < 6; k++) vel[k] = s.elapsed <= 25 ? tw[k] : 0.0f;
+                        for (int k = 0; k < 6; k++) vel[k] = s.elapsed <= 25 ? s.C[8 + k] : 0.0f;
                     }
                 }
                 A.st.va[i] = make_float4(vel[0], vel[1], vel[2], vel[3]);
@@ -384,6 +410,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_c
             iters_total += (unsigned long long)env_reset<TASK, GEOM>(c_model, s, rs, hv, row, s_k[j]);
             store_dyn<TASK>(A.st, i, s);
             store_E<TASK>(A.st, i, s.E);
+            store_hot<TASK>(A.st, i, s);
         }
         __syncwarp();
         // new rows -> global, one row at a time (rows of reset envs are scattered)
@@ -425,7 +452,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_observe_kernel(const __grid
     if (i >= A.n) return;
     EnvState s;
     load_dyn<TASK>(A.st, i, s);
-    load_E<TASK>(A.st, i, s.E);
+    load_hot<TASK>(A.st, i, s);
     float stale[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     if (TT::DYN) {
         float4 a = A.st.va[i]; float2 b = A.st.vb[i];
@@ -434,6 +461,17 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_observe_kernel(const __grid
     float row[TT::OBS];
     env_observe<TASK, GEOM_CAPSULE>(c_model, s, stale, row);
     write_rows<TASK>(A, i, row);
+}
+
+// rebuild the hot planes from the episode constants E (after urgym_set_state wrote a goal / obstacle field)
+template <int TASK>
+__global__ void __launch_bounds__(URGYM_BLOCK) urgym_derive_kernel(const AuxArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * URGYM_BLOCK + threadIdx.x;
+    if (i >= A.n) return;
+    EnvState s;
+    load_E<TASK>(A.st, i, s.E);
+    derive_cache<TASK>(s.E, s.C);
+    store_hot<TASK>(A.st, i, s);
 }
 
 template <int TASK, int GEOM>
@@ -445,7 +483,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_refresh_kernel(const __grid
     if (i >= A.n) return;
     EnvState s;
     load_dyn<TASK>(A.st, i, s);
-    load_E<TASK>(A.st, i, s.E);
+    load_hot<TASK>(A.st, i, s);
     float scratch[URGYM_SCRATCH_FLOATS];
     const bool coll = env_refresh<TASK, GEOM>(c_model, s, hv, scratch, 1);
     store_dyn<TASK>(A.st, i, s);
@@ -483,6 +521,11 @@ template <int TASK, int GEOM> cudaError_t prepare_kernels(const ModelConst &, co
 
 template <int TASK> cudaError_t launch_observe(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     urgym_observe_kernel<TASK><<<grid_for(A.n), URGYM_BLOCK, 0, s>>>(M, A);
+    return cudaGetLastError();
+}
+
+template <int TASK> cudaError_t launch_derive(const ModelConst &, const AuxArgs &A, cudaStream_t s) {
+    urgym_derive_kernel<TASK><<<grid_for(A.n), URGYM_BLOCK, 0, s>>>(A);
     return cudaGetLastError();
 }
 
