@@ -231,22 +231,18 @@ def run_ours(args, rank, world, local_rank):
     ms_max = float(t.item())
     value = n * world * steps / (ms_max * 1e-3)
 
-    # per-kernel durations, measured live with CUDA events in a short eager loop: auto-reset switched off so that
-    # urgym_step launches the step kernel alone, followed by an explicit reset of the finished envs
-    ks = max(8, min(32, steps))
-    env.L.urgym_set_autoreset(env.h, 0)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(ks)]
-    n_done_probe = 0
+    # per-kernel durations, measured live with CUDA events recorded by the library on the launching stream directly
+    # around each kernel (urgym_profile_enable), over a queue of back-to-back eager steps (one chain, serial kernels)
+    import ctypes
+    ks = max(8, min(64, steps))
+    env.L.urgym_profile_enable(env.h, 1)
     for k in range(ks):
-        ev[k][0].record(); env.step(ring[k % 8]); ev[k][1].record()
-        done = (env.terminated | env.truncated)
-        ev[k][2].record(); env.reset(mask=done); ev[k][3].record()
-        n_done_probe += int(done.sum().item())
-    torch.cuda.synchronize(dev)
-    env.L.urgym_set_autoreset(env.h, 1)
+        env.step(ring[k % 8])
+    a_ms, b_ms, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    env.L.urgym_profile_read(env.h, ctypes.byref(a_ms), ctypes.byref(b_ms), ctypes.byref(cnt))
+    env.L.urgym_profile_enable(env.h, 0)
     env.stats(reset=True)
-    t_step_kernel = sum(e[0].elapsed_time(e[1]) for e in ev) / ks          # ms
-    t_reset_kernel = sum(e[2].elapsed_time(e[3]) for e in ev) / ks
+    t_step_kernel, t_reset_kernel = a_ms.value, b_ms.value          # ms
 
     # roofline: algorithmic bytes per launch / that kernel's average launch duration
     peaks = {}

@@ -151,6 +151,13 @@ int urgym_set_event(urgym_env_t *h, uint32_t event);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t urgym_launch_count(const urgym_env_t *h);
 
+/* Kernel timing for the roofline report.  While enabled, urgym_step / urgym_step_range record CUDA events on the
+ * launching stream directly before and after the step kernel and after the auto-reset kernel (up to 256 steps are
+ * kept; not to be used while a stream is being captured).  urgym_profile_read synchronises the device and returns
+ * the average duration of the two kernels in milliseconds over the recorded steps, then clears the record. */
+int urgym_profile_enable(urgym_env_t *h, int enabled);
+int urgym_profile_read(urgym_env_t *h, double *step_kernel_ms, double *reset_kernel_ms, int *steps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions",
 EXPORTS = ["urgym_step_range", "urgym_create", "urgym_destroy", "urgym_last_error", "urgym_obs_dim", "urgym_goal_dim", "urgym_num_envs",
            "urgym_step", "urgym_reset", "urgym_observe", "urgym_refresh", "urgym_get_state", "urgym_set_state",
            "urgym_stats", "urgym_step_host", "urgym_reset_host", "urgym_set_autoreset", "urgym_get_event",
-           "urgym_set_event", "urgym_set_seed", "urgym_launch_count"]
+           "urgym_set_event", "urgym_set_seed", "urgym_launch_count", "urgym_profile_enable", "urgym_profile_read"]
 
 
 class UrgymError(RuntimeError):
@@ -58,6 +58,8 @@ def lib():
         L.urgym_set_event.argtypes = [vp, u32]
         L.urgym_set_seed.argtypes = [vp, u64]
         L.urgym_launch_count.argtypes = [vp]; L.urgym_launch_count.restype = i64
+        L.urgym_profile_enable.argtypes = [vp, i32]
+        L.urgym_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
         _lib = L
     return _lib
 

@@ -82,6 +82,9 @@ struct urgym_env {
     ModelConst model;
     void *pool;
     unsigned long long *stats;
+    int *queue;             // auto-reset queue: local indices of the envs the last step finished (a chain uses the
+                            // entries of its own env range)
+    unsigned *qcount;       // per chain: [0] queue entries, [1] block tickets of the auto-reset kernel
     float4 *hull;
     int64_t launches;
     // staging for the host-buffer entry points
@@ -90,6 +93,9 @@ struct urgym_env {
     cudaEvent_t ev_fork, ev_join[3];
     void *dstage;
     size_t dstage_bytes;
+    // kernel timing (urgym_profile_enable): event triples around the step and auto-reset kernels
+    int profiling, prof_n;
+    cudaEvent_t prof_ev[256][3];
     char err[512];
 };
 
@@ -124,6 +130,9 @@ static const step_launcher_t k_step[2][4] = {
 static const aux_launcher_t k_reset[2][4] = {
     {urgym_inst_reset_0_0, urgym_inst_reset_1_0, urgym_inst_reset_2_0, urgym_inst_reset_3_0},
     {urgym_inst_reset_0_1, urgym_inst_reset_1_1, urgym_inst_reset_2_1, urgym_inst_reset_3_1}};
+static const aux_launcher_t k_autoreset[2][4] = {
+    {urgym_inst_autoreset_0_0, urgym_inst_autoreset_1_0, urgym_inst_autoreset_2_0, urgym_inst_autoreset_3_0},
+    {urgym_inst_autoreset_0_1, urgym_inst_autoreset_1_1, urgym_inst_autoreset_2_1, urgym_inst_autoreset_3_1}};
 static const aux_launcher_t k_refresh[2][4] = {
     {urgym_inst_refresh_0_0, urgym_inst_refresh_1_0, urgym_inst_refresh_2_0, urgym_inst_refresh_3_0},
     {urgym_inst_refresh_0_1, urgym_inst_refresh_1_1, urgym_inst_refresh_2_1, urgym_inst_refresh_3_1}};
@@ -166,8 +175,8 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
         // planes: 16-byte groups first, all 256-byte aligned
         const size_t n = (size_t)n_envs;
         const size_t p16 = align_up(n * 16, 256), p8 = align_up(n * 8, 256), p4 = align_up(n * 4, 256);
-        const size_t total = 3 * p16 + p4 + 4 * p16 + p8 + p4 + p16 + p8 + 5 * p16 + p8 + p4 +
-                             URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8 + 256;
+        const size_t total = 3 * p16 + p4 + 4 * p16 + p8 + p4 + p16 + p8 + 5 * p16 + p8 + p4 + p4 +
+                             URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8 + 256 + 256;
         if ((e = cudaMalloc(&h->pool, total)) != cudaSuccess) { rc = URGYM_ENOMEM; break; }
         if ((e = cudaMemset(h->pool, 0, total)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
         char *p = (char *)h->pool;
@@ -183,8 +192,10 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
         for (int g = 0; g < 5; g++) { h->st.h4[g] = (float4 *)p; p += p16; }
         h->st.h2 = (float2 *)p; p += p8;
         h->st.h1 = (float *)p; p += p4;
+        h->queue = (int *)p; p += p4;
         h->stats = (unsigned long long *)p; p += URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8;
-        h->d_event = (uint32_t *)p;
+        h->d_event = (uint32_t *)p; p += 256;
+        h->qcount = (unsigned *)p;
         {
             AuxArgs dummy;
             memset(&dummy, 0, sizeof(dummy));
@@ -225,6 +236,9 @@ extern "C" int urgym_destroy(urgym_env_t *h) {
         if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->prof_ev[0][0])
+        for (int k = 0; k < 256; k++)
+            for (int j = 0; j < 3; j++) if (h->prof_ev[k][j]) cudaEventDestroy(h->prof_ev[k][j]);
     if (h->dstage) cudaFree(h->dstage);
     if (h->hull) cudaFree(h->hull);
     if (h->pool) cudaFree(h->pool);
@@ -271,7 +285,7 @@ static StateView view_at(const StateView &v, int64_t off) {
 }
 
 // one env step of the envs [first, first + count) (array pointers are those of the WHOLE arrays)
-static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, int chain, const float *actions, float *obs, float *achieved,
+static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, int chain, int qslot, const float *actions, float *obs, float *achieved,
                       float *desired, float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
                       float *terminal_obs, float *terminal_achieved, cudaStream_t stream) {
     const int D = obs_dim(h->task), G = goal_dim(h->task);
@@ -281,21 +295,55 @@ static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, int 
     A.ach = achieved ? achieved + first * G : nullptr; A.des = desired ? desired + first * G : nullptr;
     A.rew = reward + first; A.term = terminated + first; A.trunc = truncated + first; A.succ = is_success + first;
     A.stats = h->stats; A.event = h->d_event; A.bump = bump; A.chain = chain; A.hull = h->hull;
+    A.queue = h->autoreset ? h->queue + first : nullptr;
+    A.qcount = h->qcount + 2 * qslot;     // ranges in flight at the same time use different slots
+    const bool prof = h->profiling && h->prof_n < 256;
+    if (prof) CK(cudaEventRecord(h->prof_ev[h->prof_n][0], stream));
     CK(k_step[h->geom][h->task](h->model, A, stream));
     h->launches++;
+    if (prof) CK(cudaEventRecord(h->prof_ev[h->prof_n][1], stream));
     if (h->autoreset) {
-        // the finished envs (terminated | truncated) restart in a second, dense kernel
+        // the finished envs (terminated | truncated), queued by the step kernel, restart in a second, dense kernel
         AuxArgs R;
         memset(&R, 0, sizeof(R));
         R.st = A.st; R.n = count; R.offset = h->offset + first; R.key = key_of(h->seed);
-        R.mask = A.term; R.mask2 = A.trunc; R.autoreset = 1;
+        R.queue = A.queue; R.qcount = A.qcount; R.autoreset = 1;
         R.obs = A.obs; R.ach = A.ach; R.des = A.des;
         R.tobs = terminal_obs ? terminal_obs + first * D : nullptr;
         R.tach = terminal_achieved ? terminal_achieved + first * G : nullptr;
         R.stats = h->stats; R.event = h->d_event; R.chain = chain; R.hull = h->hull;
-        CK(k_reset[h->geom][h->task](h->model, R, stream));
+        CK(k_autoreset[h->geom][h->task](h->model, R, stream));
         h->launches++;
     }
+    if (prof) { CK(cudaEventRecord(h->prof_ev[h->prof_n][2], stream)); h->prof_n++; }
+    return URGYM_OK;
+}
+
+extern "C" int urgym_profile_enable(urgym_env_t *h, int enabled) {
+    if (!h) return URGYM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if (enabled && !h->prof_ev[0][0])
+        for (int k = 0; k < 256; k++)
+            for (int j = 0; j < 3; j++) CK(cudaEventCreate(&h->prof_ev[k][j]));
+    h->profiling = enabled ? 1 : 0;
+    h->prof_n = 0;
+    return URGYM_OK;
+}
+extern "C" int urgym_profile_read(urgym_env_t *h, double *step_kernel_ms, double *reset_kernel_ms, int *steps) {
+    if (!h || !step_kernel_ms || !reset_kernel_ms || !steps) return URGYM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < h->prof_n; k++) {
+        float x = 0.0f, y = 0.0f;
+        CK(cudaEventElapsedTime(&x, h->prof_ev[k][0], h->prof_ev[k][1]));
+        CK(cudaEventElapsedTime(&y, h->prof_ev[k][1], h->prof_ev[k][2]));
+        a += x; b += y;
+    }
+    *steps = h->prof_n;
+    *step_kernel_ms = h->prof_n ? a / h->prof_n : 0.0;
+    *reset_kernel_ms = h->prof_n ? b / h->prof_n : 0.0;
+    h->prof_n = 0;
     return URGYM_OK;
 }
 
@@ -308,7 +356,7 @@ extern "C" int urgym_step_range(urgym_env_t *h, int64_t first, int64_t count, in
     if (first < 0 || count <= 0 || first + count > h->n || chain < 0 || chain >= URGYM_MAX_CHAINS)
         return fail(h, URGYM_EINVAL, "urgym_step_range: range or chain out of bounds%s", "");
     CK(cudaSetDevice(h->device));
-    return step_range(h, first, count, 1, chain, actions, obs, achieved, desired, reward, terminated, truncated, is_success,
+    return step_range(h, first, count, 1, chain, chain, actions, obs, achieved, desired, reward, terminated, truncated, is_success,
                       terminal_obs, terminal_achieved, (cudaStream_t)stream);
 }
 
@@ -319,7 +367,7 @@ extern "C" int urgym_step(urgym_env_t *h, const float *actions, float *obs, floa
     if (!actions || !obs || !reward || !terminated || !truncated || !is_success)
         return fail(h, URGYM_EINVAL, "urgym_step: actions, obs, reward, terminated, truncated, is_success must not be NULL%s", "");
     CK(cudaSetDevice(h->device));
-    return step_range(h, 0, h->n, 2, 0, actions, obs, achieved, desired, reward, terminated, truncated, is_success,
+    return step_range(h, 0, h->n, 2, 0, 0, actions, obs, achieved, desired, reward, terminated, truncated, is_success,
                       terminal_obs, terminal_achieved, (cudaStream_t)stream);
 }
 
@@ -457,7 +505,7 @@ extern "C" int urgym_step_host(urgym_env_t *h, const float *actions, float *obs,
         cudaStream_t s = h->cstream[k % 3];
         if (k < 3) { CK(cudaStreamWaitEvent(s, h->ev_fork, 0)); used = k + 1; }
         CK(cudaMemcpyAsync(d_act + first * 6, actions + first * 6, (size_t)cnt * 6 * 4, cudaMemcpyHostToDevice, s));
-        rc = step_range(h, first, cnt, 0, 0, d_act, d_obs, achieved ? d_ach : nullptr, desired ? d_des : nullptr, d_rew, d_term,
+        rc = step_range(h, first, cnt, 0, 0, k % 3, d_act, d_obs, achieved ? d_ach : nullptr, desired ? d_des : nullptr, d_rew, d_term,
                         d_trunc, d_succ, terminal_obs ? d_tobs : nullptr, terminal_achieved ? d_tach : nullptr, s);
         if (rc != URGYM_OK) return rc;
         CK(cudaMemcpyAsync(obs + first * D, d_obs + first * D, (size_t)cnt * D * 4, cudaMemcpyDeviceToHost, s));

@@ -13,6 +13,9 @@ cudaError_t NAME(urgym_inst_step_, URGYM_INST_TASK, URGYM_INST_GEOM)(const Model
 cudaError_t NAME(urgym_inst_reset_, URGYM_INST_TASK, URGYM_INST_GEOM)(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     return launch_reset<URGYM_INST_TASK, URGYM_INST_GEOM>(M, A, s);
 }
+cudaError_t NAME(urgym_inst_autoreset_, URGYM_INST_TASK, URGYM_INST_GEOM)(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
+    return launch_autoreset<URGYM_INST_TASK, URGYM_INST_GEOM>(M, A, s);
+}
 cudaError_t NAME(urgym_inst_refresh_, URGYM_INST_TASK, URGYM_INST_GEOM)(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     return launch_refresh<URGYM_INST_TASK, URGYM_INST_GEOM>(M, A, s);
 }

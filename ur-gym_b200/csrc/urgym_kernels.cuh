@@ -129,6 +129,8 @@ struct StepArgs {
     int bump;                   // 0: none (the caller bumped), 1: this chain's counter, 2: all counters (a whole step)
     int chain;
     const float4 *hull;
+    int *queue;                 // auto-reset queue of this chain: local indices of the envs this step finished (or NULL)
+    unsigned *qcount;           // its entry count
 };
 
 __device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -216,6 +218,10 @@ __global__ void __launch_bounds__(URGYM_BLOCK, URGYM_STEP_MINBLOCKS) urgym_step_
         }
         if (lane == 0) stat_add(slot + 6, (unsigned long long)rows);
     }
+    // auto-reset queue: one reservation per warp that finished envs (the reply is needed only at the very end)
+    const unsigned done_mask = __ballot_sync(0xffffffffu, live && (o.terminated || o.truncated));
+    unsigned qbase = 0u;
+    if (A.queue && done_mask && lane == 0) qbase = atomicAdd(A.qcount, (unsigned)__popc(done_mask));
     __syncwarp();
     // observation tile -> global, 16-byte vectorised
     float *gobs = A.obs + wbase * D;
@@ -241,6 +247,10 @@ __global__ void __launch_bounds__(URGYM_BLOCK, URGYM_STEP_MINBLOCKS) urgym_step_
             for (int k = 0; k < G; k++) g[k] = row[12 + k];
         }
     }
+    if (A.queue && done_mask) {
+        qbase = __shfl_sync(0xffffffffu, qbase, 0);
+        if ((done_mask >> lane) & 1u) A.queue[qbase + __popc(done_mask & ((1u << lane) - 1u))] = (int)(wbase + lane);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ reset / auto-reset
@@ -257,6 +267,8 @@ struct AuxArgs {
     const uint32_t *event;
     int chain;
     const float4 *hull;
+    const int *queue;               // auto-reset kernel: the step kernel's queue of finished envs
+    unsigned *qcount;               // [0] entries, [1] block tickets of the auto-reset kernel
 };
 
 #ifndef URGYM_RESET_GROUP
@@ -264,77 +276,19 @@ struct AuxArgs {
                                        rate (measured on B200, Dyn 1 Mi envs: 128 -> 0.205, 256 -> 0.199, 512 -> 0.215 ms per step) */
 #endif
 
-// RobotTaskEnv.reset for the envs selected by the masks (core.py:263-273), in dense form: every warp scans 128
-// consecutive envs, compacts the selected ones with warp ballots, and resets them 32 at a time, one env per lane.
-// ReachDyn's rejection loop accepts only ~17.5 % of its draws on the cheap start-end distance rule, so that part
-// of the search runs 4 iterations per env in parallel (4-lane groups, 8 envs per pass) before the lane-per-env
-// phase evaluates the surviving iteration completely.
+// RobotTaskEnv.reset (core.py:263-273) of `cnt` envs listed in s_list (indices relative to gbase), by one warp, 32 at a
+// time with one env per lane.  ReachDyn's rejection loop accepts only ~17.5 % of its draws on the cheap start-end
+// distance rule, so that part of the search runs 4 iterations per env in parallel (4-lane groups, 8 envs per pass)
+// before the lane-per-env phase evaluates the surviving iteration completely.  Returns this lane's share of the
+// rejection iterations used.
 template <int TASK, int GEOM>
-__global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
+__device__ __forceinline__ unsigned long long reset_listed(const ModelConst &c_model, const AuxArgs &A, const float4 *hv, int lane,
+                                                           int64_t gbase, const int *s_list, int *s_k, float *s_rows, int cnt,
+                                                           uint32_t event) {
     typedef Traits<TASK> TT;
-    constexpr int D = TT::OBS, G = TT::GOAL, W = 32, NW = URGYM_BLOCK / 32;
-    extern __shared__ float4 smem4[];
-    float *s_rows_all = reinterpret_cast<float *>(smem4);                    // [NW][32][D] new observation rows
-    int *s_list_all = reinterpret_cast<int *>(s_rows_all + NW * W * D);      // [NW][128] selected envs (local index)
-    int *s_k_all = s_list_all + NW * URGYM_RESET_GROUP;                      // [NW][128] first iteration to evaluate
-    float4 *s_hull = reinterpret_cast<float4 *>(s_k_all + NW * URGYM_RESET_GROUP);
-    const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
-    if (GEOM == GEOM_HULL) __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *s_rows = s_rows_all + warp * W * D;
-    int *s_list = s_list_all + warp * URGYM_RESET_GROUP, *s_k = s_k_all + warp * URGYM_RESET_GROUP;
-    const int64_t gbase = ((int64_t)blockIdx.x * NW + warp) * URGYM_RESET_GROUP;
-    if (gbase >= A.n) return;
-    const uint32_t event = A.event[A.chain];
-
-    // 1. compaction of the selected envs of this group: each lane reads the mask bytes of its GROUP/32 consecutive envs as
-    //    32-bit words (the compiler merges them into one 16-byte load per mask array), a warp scan of the per-lane counts places the entries
-    int cnt = 0;
-    {
-        constexpr int PER = URGYM_RESET_GROUP / W;      // 16 envs per lane
-        const int64_t i0 = gbase + (int64_t)lane * PER;
-        unsigned bits = 0;
-        const bool vec_ok = (i0 + PER <= A.n) && ((gbase & 15) == 0) &&
-                            (!A.mask || aligned16(A.mask)) && (!A.mask2 || aligned16(A.mask2));
-        if (A.mask == nullptr && A.mask2 == nullptr) {
-            for (int k = 0; k < PER; k++) if (i0 + k < A.n) bits |= 1u << k;
-        } else if (vec_ok) {
-            unsigned w[PER / 4];
-#pragma unroll
-            for (int k = 0; k < PER / 4; k++) {
-                w[k] = 0u;
-                if (A.mask) w[k] |= reinterpret_cast<const unsigned *>(A.mask + i0)[k];
-                if (A.mask2) w[k] |= reinterpret_cast<const unsigned *>(A.mask2 + i0)[k];
-            }
-#pragma unroll
-            for (int k = 0; k < PER; k++) if ((w[k >> 2] >> (8 * (k & 3))) & 0xFFu) bits |= 1u << k;
-        } else {
-            for (int k = 0; k < PER; k++) {
-                const int64_t i = i0 + k;
-                if (i < A.n && ((A.mask && A.mask[i]) || (A.mask2 && A.mask2[i]))) bits |= 1u << k;
-            }
-        }
-        const int mine = __popc(bits);
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < W; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        cnt = __shfl_sync(0xffffffffu, incl, W - 1);
-        int pos = incl - mine;
-        while (bits) {
-            const int k = __ffs(bits) - 1;
-            bits &= bits - 1;
-            s_list[pos++] = lane * PER + k;
-        }
-    }
-    if (cnt == 0) return;
-    __syncwarp();
-
-    // 2. auto-reset: the rows still hold the final observation of the finished episodes -> terminal observation
-    //    (flattened over (row, column) so that several independent loads are in flight per lane)
+    constexpr int D = TT::OBS, G = TT::GOAL, W = 32;
+    // auto-reset: the rows still hold the final observation of the finished episodes -> terminal observation
+    // (flattened over (row, column) so that several independent loads are in flight per lane)
     if (A.autoreset && (A.tobs || A.tach)) {
 #pragma unroll 4
         for (int k = lane; k < cnt * D; k += W) {
@@ -346,7 +300,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_c
         }
     }
 
-    // 3. ReachDyn: first iteration that passes the start-end distance rule, 4 candidate iterations per env at a time
+    // ReachDyn: first iteration that passes the start-end distance rule, 4 candidate iterations per env at a time
     for (int j = lane; j < cnt; j += W) s_k[j] = 0;
     __syncwarp();
     if (TT::DYN) {
@@ -374,7 +328,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_c
         __syncwarp();
     }
 
-    // 4. one env per lane: complete sample from iteration s_k on, neutral pose, link distances, first observation
+    // one env per lane: complete sample from iteration s_k on, neutral pose, link distances, first observation
     unsigned long long iters_total = 0ull;
     for (int j0 = 0; j0 < cnt; j0 += W) {
         const int j = j0 + lane;
@@ -427,9 +381,123 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_c
         }
         __syncwarp();
     }
+    return iters_total;
+}
+
+// Reset of the envs selected by up to two byte masks: every warp scans URGYM_RESET_GROUP consecutive envs, compacts the
+// selected ones with a warp scan and resets them (reset_listed).
+template <int TASK, int GEOM>
+__global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
+    typedef Traits<TASK> TT;
+    constexpr int D = TT::OBS, W = 32, NW = URGYM_BLOCK / 32;
+    extern __shared__ float4 smem4[];
+    float *s_rows_all = reinterpret_cast<float *>(smem4);                    // [NW][32][D] new observation rows
+    int *s_list_all = reinterpret_cast<int *>(s_rows_all + NW * W * D);      // [NW][GROUP] selected envs (local index)
+    int *s_k_all = s_list_all + NW * URGYM_RESET_GROUP;                      // [NW][GROUP] first iteration to evaluate
+    float4 *s_hull = reinterpret_cast<float4 *>(s_k_all + NW * URGYM_RESET_GROUP);
+    const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
+    if (GEOM == GEOM_HULL) __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *s_rows = s_rows_all + warp * W * D;
+    int *s_list = s_list_all + warp * URGYM_RESET_GROUP, *s_k = s_k_all + warp * URGYM_RESET_GROUP;
+    const int64_t gbase = ((int64_t)blockIdx.x * NW + warp) * URGYM_RESET_GROUP;
+    if (gbase >= A.n) return;
+    const uint32_t event = A.event[A.chain];
+
+    // compaction of the selected envs of this group: each lane reads the mask bytes of its GROUP/32 consecutive envs as
+    // 32-bit words (the compiler merges them into one 16-byte load per mask array), a warp scan of the per-lane counts places the entries
+    int cnt = 0;
+    {
+        constexpr int PER = URGYM_RESET_GROUP / W;
+        const int64_t i0 = gbase + (int64_t)lane * PER;
+        unsigned bits = 0;
+        const bool vec_ok = (i0 + PER <= A.n) && ((gbase & 15) == 0) &&
+                            (!A.mask || aligned16(A.mask)) && (!A.mask2 || aligned16(A.mask2));
+        if (A.mask == nullptr && A.mask2 == nullptr) {
+            for (int k = 0; k < PER; k++) if (i0 + k < A.n) bits |= 1u << k;
+        } else if (vec_ok) {
+            unsigned w[PER / 4];
+#pragma unroll
+            for (int k = 0; k < PER / 4; k++) {
+                w[k] = 0u;
+                if (A.mask) w[k] |= reinterpret_cast<const unsigned *>(A.mask + i0)[k];
+                if (A.mask2) w[k] |= reinterpret_cast<const unsigned *>(A.mask2 + i0)[k];
+            }
+#pragma unroll
+            for (int k = 0; k < PER; k++) if ((w[k >> 2] >> (8 * (k & 3))) & 0xFFu) bits |= 1u << k;
+        } else {
+            for (int k = 0; k < PER; k++) {
+                const int64_t i = i0 + k;
+                if (i < A.n && ((A.mask && A.mask[i]) || (A.mask2 && A.mask2[i]))) bits |= 1u << k;
+            }
+        }
+        const int mine = __popc(bits);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < W; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        cnt = __shfl_sync(0xffffffffu, incl, W - 1);
+        int pos = incl - mine;
+        while (bits) {
+            const int k = __ffs(bits) - 1;
+            bits &= bits - 1;
+            s_list[pos++] = lane * PER + k;
+        }
+    }
+    if (cnt == 0) return;
+    __syncwarp();
+    unsigned long long iters_total = reset_listed<TASK, GEOM>(c_model, A, hv, lane, gbase, s_list, s_k, s_rows, cnt, event);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) iters_total += __shfl_xor_sync(0xffffffffu, iters_total, o);
     if (lane == 0) atomicAdd(&A.stats[(blockIdx.x % URGYM_STAT_SLOTS) * URGYM_STATS_COUNT + 7], iters_total);
+}
+
+// Auto-reset after a step: the step kernel has queued the (local) indices of the finished envs (StepArgs::queue), so the
+// lanes are dense here: every warp takes 32 queue entries at a time.  The last block to finish empties the queue counter
+// for the next step.
+template <int TASK, int GEOM>
+__global__ void __launch_bounds__(URGYM_BLOCK) urgym_autoreset_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
+    typedef Traits<TASK> TT;
+    constexpr int D = TT::OBS, W = 32, NW = URGYM_BLOCK / 32;
+    extern __shared__ float4 smem4[];
+    float *s_rows_all = reinterpret_cast<float *>(smem4);                    // [NW][32][D] new observation rows
+    int *s_list_all = reinterpret_cast<int *>(s_rows_all + NW * W * D);      // [NW][32]
+    int *s_k_all = s_list_all + NW * W;                                      // [NW][32]
+    float4 *s_hull = reinterpret_cast<float4 *>(s_k_all + NW * W);
+    const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
+    if (GEOM == GEOM_HULL) __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *s_rows = s_rows_all + warp * W * D;
+    int *s_list = s_list_all + warp * W, *s_k = s_k_all + warp * W;
+    const uint32_t event = A.event[A.chain];
+    const int total = (int)*A.qcount;
+    const int nwarps = gridDim.x * NW;
+    unsigned long long iters_total = 0ull;
+    for (int base = (blockIdx.x * NW + warp) * W; base < total; base += nwarps * W) {
+        const int cnt = min(W, total - base);
+        if (lane < cnt) s_list[lane] = A.queue[base + lane];
+        __syncwarp();
+        iters_total += reset_listed<TASK, GEOM>(c_model, A, hv, lane, 0, s_list, s_k, s_rows, cnt, event);
+    }
+    if ((blockIdx.x * NW + warp) * W < total) {        // warp-uniform: this warp reset something
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) iters_total += __shfl_xor_sync(0xffffffffu, iters_total, o);
+        if (lane == 0) atomicAdd(&A.stats[(blockIdx.x % URGYM_STAT_SLOTS) * URGYM_STATS_COUNT + 7], iters_total);
+    }
+    // every block has read the counter before it takes its ticket; the last ticket holder clears both
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(A.qcount + 1, 1u);
+        if (t == gridDim.x - 1) { A.qcount[0] = 0u; A.qcount[1] = 0u; }
+    }
+}
+template <int TASK, int GEOM> constexpr size_t autoreset_smem_bytes() {
+    return (size_t)URGYM_BLOCK * Traits<TASK>::OBS * sizeof(float) + 2 * URGYM_BLOCK * sizeof(int) +
+           (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
 template <int TASK, int GEOM> constexpr size_t reset_smem_bytes() {
     return (size_t)URGYM_BLOCK * Traits<TASK>::OBS * sizeof(float) + 2 * (URGYM_BLOCK / 32) * URGYM_RESET_GROUP * sizeof(int) +
@@ -502,6 +570,12 @@ template <int TASK, int GEOM> cudaError_t launch_reset(const ModelConst &M, cons
     urgym_reset_kernel<TASK, GEOM><<<(unsigned)((A.n + per_block - 1) / per_block), URGYM_BLOCK, reset_smem_bytes<TASK, GEOM>(), s>>>(M, A);
     return cudaGetLastError();
 }
+template <int TASK, int GEOM> cudaError_t launch_autoreset(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
+    // enough warps for ~1/8 of the envs finishing in one step; beyond that the warps loop
+    const int64_t blocks = (A.n + 8 * URGYM_BLOCK - 1) / (8 * URGYM_BLOCK);
+    urgym_autoreset_kernel<TASK, GEOM><<<(unsigned)blocks, URGYM_BLOCK, autoreset_smem_bytes<TASK, GEOM>(), s>>>(M, A);
+    return cudaGetLastError();
+}
 template <int TASK, int GEOM> cudaError_t launch_refresh(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     const size_t smem = GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
     urgym_refresh_kernel<TASK, GEOM><<<grid_for(A.n), URGYM_BLOCK, smem, s>>>(M, A);
@@ -513,6 +587,8 @@ template <int TASK, int GEOM> cudaError_t prepare_kernels(const ModelConst &, co
     cudaError_t e = cudaFuncSetAttribute(urgym_step_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes<TASK, GEOM>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(urgym_reset_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reset_smem_bytes<TASK, GEOM>());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(urgym_autoreset_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)autoreset_smem_bytes<TASK, GEOM>());
     if (e != cudaSuccess) return e;
     const size_t smem = GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
     if (smem) e = cudaFuncSetAttribute(urgym_refresh_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -535,6 +611,7 @@ typedef cudaError_t (*aux_launcher_t)(const ModelConst &, const AuxArgs &, cudaS
 #define URGYM_DECLARE_INST(T, G)                                                           \
     cudaError_t urgym_inst_step_##T##_##G(const ModelConst &, const StepArgs &, cudaStream_t);   \
     cudaError_t urgym_inst_reset_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);   \
+    cudaError_t urgym_inst_autoreset_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);   \
     cudaError_t urgym_inst_refresh_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);      \
     cudaError_t urgym_inst_prepare_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);
 URGYM_DECLARE_INST(0, 0) URGYM_DECLARE_INST(1, 0) URGYM_DECLARE_INST(2, 0) URGYM_DECLARE_INST(3, 0)
