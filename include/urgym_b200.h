@@ -98,7 +98,7 @@ int urgym_step(urgym_env_t *h, const float *actions, float *obs, float *achieved
 
 /* The same step for the envs [first, first + count) only (array pointers are those of the WHOLE arrays).  Lets a caller
  * advance disjoint env ranges as independent "chains" on different streams, so that one range's auto-reset kernel
- * overlaps another range's step kernel.  Each chain (0..3) counts its own reset events: a chain must be stepped as
+ * overlaps another range's step kernel.  Each chain (0..7) counts its own reset events: a chain must be stepped as
  * often as the others before the next whole-batch urgym_step / urgym_reset, and always with the same range.
  * Results are identical to urgym_step over the whole batch. */
 int urgym_step_range(urgym_env_t *h, int64_t first, int64_t count, int chain, const float *actions, float *obs,

@@ -293,6 +293,8 @@ static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, int 
     A.st = view_at(h->st, first); A.n = count;
     A.actions = actions + first * 6; A.obs = obs + first * D;
     A.ach = achieved ? achieved + first * G : nullptr; A.des = desired ? desired + first * G : nullptr;
+    A.tobs = (h->autoreset && terminal_obs) ? terminal_obs + first * D : nullptr;
+    A.tach = (h->autoreset && terminal_achieved) ? terminal_achieved + first * G : nullptr;
     A.rew = reward + first; A.term = terminated + first; A.trunc = truncated + first; A.succ = is_success + first;
     A.stats = h->stats; A.event = h->d_event; A.bump = bump; A.chain = chain; A.hull = h->hull;
     A.queue = h->autoreset ? h->queue + first : nullptr;
@@ -309,8 +311,7 @@ static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, int 
         R.st = A.st; R.n = count; R.offset = h->offset + first; R.key = key_of(h->seed);
         R.queue = A.queue; R.qcount = A.qcount; R.autoreset = 1;
         R.obs = A.obs; R.ach = A.ach; R.des = A.des;
-        R.tobs = terminal_obs ? terminal_obs + first * D : nullptr;
-        R.tach = terminal_achieved ? terminal_achieved + first * G : nullptr;
+        // (the step kernel has already written the terminal rows)
         R.stats = h->stats; R.event = h->d_event; R.chain = chain; R.hull = h->hull;
         CK(k_autoreset[h->geom][h->task](h->model, R, stream));
         h->launches++;

@@ -25,7 +25,7 @@
 using namespace urgym;
 
 #define URGYM_BLOCK 128
-#define URGYM_MAX_CHAINS 4     /* independent step chains (env sub-ranges advanced on their own streams) */
+#define URGYM_MAX_CHAINS 8     /* independent step chains (env sub-ranges advanced on their own streams) */
 #ifndef URGYM_STEP_MINBLOCKS
 #define URGYM_STEP_MINBLOCKS 6      /* resident step-kernel blocks per SM the register allocation is held to */
 #endif
@@ -123,6 +123,7 @@ struct StepArgs {
     int64_t n;
     const float *actions;
     float *obs, *ach, *des, *rew;
+    float *tobs, *tach;         // terminal observation / achieved goal rows of the envs this step finishes (or NULL)
     uint8_t *term, *trunc, *succ;
     unsigned long long *stats;
     uint32_t *event;            // device-resident reset-event counters, one per chain (URGYM_MAX_CHAINS)
@@ -247,6 +248,19 @@ __global__ void __launch_bounds__(URGYM_BLOCK, URGYM_STEP_MINBLOCKS) urgym_step_
             for (int k = 0; k < G; k++) g[k] = row[12 + k];
         }
     }
+    // finished envs: their rows are DummyVecEnv's terminal observation (the auto-reset kernel overwrites `obs`)
+    if (done_mask && (A.tobs || A.tach)) {
+        for (unsigned m = done_mask; m; m &= m - 1u) {
+            const int r = __ffs(m) - 1;
+            const float *row = s_obs + r * D;
+            if (A.tobs) {
+                float *g = A.tobs + (wbase + r) * D;
+                if (lane < D) g[lane] = row[lane];
+                if (lane + W < D) g[lane + W] = row[lane + W];
+            }
+            if (A.tach && lane < G) A.tach[(wbase + r) * G + lane] = row[lane];
+        }
+    }
     if (A.queue && done_mask) {
         qbase = __shfl_sync(0xffffffffu, qbase, 0);
         if ((done_mask >> lane) & 1u) A.queue[qbase + __popc(done_mask & ((1u << lane) - 1u))] = (int)(wbase + lane);
@@ -367,16 +381,21 @@ __device__ __forceinline__ unsigned long long reset_listed(const ModelConst &c_m
             store_hot<TASK>(A.st, i, s);
         }
         __syncwarp();
-        // new rows -> global, one row at a time (rows of reset envs are scattered)
-        const int nrows = min(W, cnt - j0);
-        for (int r = 0; r < nrows; r++) {
-            const int64_t i = gbase + s_list[j0 + r];
-            const float *row = s_rows + r * D;
-            for (int c = lane; c < D; c += W) {
-                const float v = row[c];
-                if (A.obs) A.obs[i * D + c] = v;
-                if (A.ach && c < G) A.ach[i * G + c] = v;
-                if (A.des && c >= 12 && c < 12 + G) A.des[i * G + c - 12] = v;
+        // new rows -> global: every lane writes its own row (the rows of reset envs are scattered anyway)
+        if (j < cnt) {
+            const int64_t i = gbase + s_list[j];
+            const float *row = s_rows + lane * D;
+            if (A.obs) {
+#pragma unroll
+                for (int c = 0; c < D; c++) A.obs[i * D + c] = row[c];
+            }
+            if (A.ach) {
+#pragma unroll
+                for (int c = 0; c < G; c++) A.ach[i * G + c] = row[c];
+            }
+            if (A.des) {
+#pragma unroll
+                for (int c = 0; c < G; c++) A.des[i * G + c] = row[12 + c];
             }
         }
         __syncwarp();
@@ -573,8 +592,18 @@ template <int TASK, int GEOM> cudaError_t launch_reset(const ModelConst &M, cons
 template <int TASK, int GEOM> cudaError_t launch_autoreset(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     // enough warps for ~1/8 of the envs finishing in one step; beyond that the warps loop
     const int64_t blocks = (A.n + 8 * URGYM_BLOCK - 1) / (8 * URGYM_BLOCK);
-    urgym_autoreset_kernel<TASK, GEOM><<<(unsigned)blocks, URGYM_BLOCK, autoreset_smem_bytes<TASK, GEOM>(), s>>>(M, A);
-    return cudaGetLastError();
+    // Highest launch priority: the kernel is short, latency-bound and sits on the critical path of its chain
+    // (step -> auto-reset -> next step), so its blocks should not queue behind the thousands of step-kernel blocks that
+    // other chains have in flight.
+    static int prio_hi = 1;
+    if (prio_hi == 1) { int lo = 0; if (cudaDeviceGetStreamPriorityRange(&lo, &prio_hi) != cudaSuccess) prio_hi = 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(URGYM_BLOCK);
+    cfg.dynamicSmemBytes = autoreset_smem_bytes<TASK, GEOM>(); cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributePriority; attr[0].val.priority = prio_hi;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, urgym_autoreset_kernel<TASK, GEOM>, M, A);
 }
 template <int TASK, int GEOM> cudaError_t launch_refresh(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     const size_t smem = GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;

@@ -118,8 +118,8 @@ class UR5VecEnv:
         for a in action_buffers:
             if a.device != self.device or a.dtype != torch.float32 or not a.is_contiguous() or a.shape != (self.num_envs, 6):
                 raise ValueError("capture_steps needs contiguous float32 [N,6] tensors on the simulator's device")
-        if not 1 <= chains <= 4:
-            raise ValueError("chains must be 1..4")
+        if not 1 <= chains <= 8:
+            raise ValueError("chains must be 1..8")
         per = -(-self.num_envs // chains)
         per = -(-per // 256) * 256                      # whole reset groups per chain
         ranges = [(f, min(per, self.num_envs - f)) for f in range(0, self.num_envs, per)]
