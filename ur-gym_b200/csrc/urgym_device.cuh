@@ -110,7 +110,10 @@ URGYM_HD float fdiv(float a, float b) {               // division where 2 ulp ar
 }
 
 // ------------------------------------------------------------------------------------------------ constants
-struct ModelConst {
+struct alignas(16) ModelConst {
+    // packed-math copies (first, so that the pairs sit 8-byte aligned in the constant bank)
+    float joint_rot_p[6][3][4]; // rows of joint_rot padded to 4: (F[k][0], F[k][1]) is a constant pair
+    float cap_pp[7][3][2];      // (cap_p0[l][k], cap_p1[l][k])
     float joint_xyz[6][3];
     float joint_rot[6][9];      // Rz(y)Ry(p)Rx(r) of each joint origin, row-major
     float cap_p0[7][3];         // bounding capsule of each link hull, link frame
@@ -153,6 +156,35 @@ URGYM_HD float3 cross(float3 a, float3 b) {
     return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 URGYM_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// ------------------------------------------------------------------------------------------------ packed FP32 pairs
+// Blackwell's FFMA2 / FMUL2 / FADD2 do two FP32 operations in one issue slot (operands are 64-bit register pairs,
+// a scalar register or constant can be broadcast to both halves).  The step kernel is bound by the issue rate, so
+// the vector math of the kinematic chain is written on pairs.  The host instantiation does the two halves in turn
+// with the same roundings.
+URGYM_HD float2 f2(float x, float y) { return make_float2(x, y); }
+URGYM_HD float2 bc2(float s) { return make_float2(s, s); }
+URGYM_HD float2 fma2(float2 a, float2 b, float2 c) {
+#ifdef __CUDA_ARCH__
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+URGYM_HD float2 mul2(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __fmul2_rn(a, b);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+URGYM_HD float2 add2(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
 
 struct Pose {           // world pose of a link frame
     float R[9];         // row-major
@@ -309,6 +341,51 @@ URGYM_HD void fk_advance(const ModelConst &M, Pose &T, int j, float qj) {
 URGYM_HD void pose_identity(Pose &T) {
     T.R[0] = 1; T.R[1] = 0; T.R[2] = 0; T.R[3] = 0; T.R[4] = 1; T.R[5] = 0; T.R[6] = 0; T.R[7] = 0; T.R[8] = 1;
     T.p = f3(0, 0, 0);
+}
+// The same chain on packed pairs.  R is kept by columns, each column as its (x, y) pair plus the z parts:
+//   ck = (R[0][k], R[1][k]) for k = 0..2,  z01 = (R[2][0], R[2][1]),  z2 = R[2][2];  position (pxy, pz).
+struct PoseP {
+    float2 c0, c1, c2, z01, pxy;
+    float z2, pz;
+};
+URGYM_HD void posep_identity(PoseP &T) {
+    T.c0 = f2(1, 0); T.c1 = f2(0, 1); T.c2 = f2(0, 0); T.z01 = f2(0, 0); T.z2 = 1; T.pxy = f2(0, 0); T.pz = 0;
+}
+URGYM_HD void fkp_advance(const ModelConst &M, PoseP &T, int j, float qj) {
+    const float *X = M.joint_xyz[j];
+    const float (*F)[4] = M.joint_rot_p[j];
+    T.pxy = fma2(T.c0, bc2(X[0]), fma2(T.c1, bc2(X[1]), fma2(T.c2, bc2(X[2]), T.pxy)));
+    T.pz = fmaf(T.z01.x, X[0], fmaf(T.z01.y, X[1], fmaf(T.z2, X[2], T.pz)));
+    // A = R F: (x, y) parts of the three columns, then the z parts ((A20, A21) as a pair)
+    const float2 a0 = fma2(T.c0, bc2(F[0][0]), fma2(T.c1, bc2(F[1][0]), mul2(T.c2, bc2(F[2][0]))));
+    const float2 a1 = fma2(T.c0, bc2(F[0][1]), fma2(T.c1, bc2(F[1][1]), mul2(T.c2, bc2(F[2][1]))));
+    const float2 a2 = fma2(T.c0, bc2(F[0][2]), fma2(T.c1, bc2(F[1][2]), mul2(T.c2, bc2(F[2][2]))));
+    const float2 az = fma2(bc2(T.z01.x), f2(F[0][0], F[0][1]),
+                           fma2(bc2(T.z01.y), f2(F[1][0], F[1][1]), mul2(bc2(T.z2), f2(F[2][0], F[2][1]))));
+    const float az2 = fmaf(T.z01.x, F[0][2], fmaf(T.z01.y, F[1][2], T.z2 * F[2][2]));
+    float s, c;
+    sincos_fast(qj, &s, &c);
+    T.c0 = fma2(a0, bc2(c), mul2(a1, bc2(s)));
+    T.c1 = fma2(a1, bc2(c), mul2(a0, bc2(-s)));
+    T.c2 = a2;
+    T.z01 = f2(fmaf(az.x, c, az.y * s), fmaf(az.y, c, -az.x * s));
+    T.z2 = az2;
+}
+// world capsule segment of link l: a = p + R cap_p0, b = p + R cap_p1; returns (a.x, a.y), (b.x, b.y), (a.z, b.z)
+URGYM_HD void capsule_world(const ModelConst &M, const PoseP &T, int l, float2 &axy, float2 &bxy, float2 &abz) {
+    const float (*P)[2] = M.cap_pp[l];
+    axy = fma2(T.c0, bc2(P[0][0]), fma2(T.c1, bc2(P[1][0]), fma2(T.c2, bc2(P[2][0]), T.pxy)));
+    bxy = fma2(T.c0, bc2(P[0][1]), fma2(T.c1, bc2(P[1][1]), fma2(T.c2, bc2(P[2][1]), T.pxy)));
+    abz = fma2(bc2(T.z01.x), f2(P[0][0], P[0][1]),
+               fma2(bc2(T.z01.y), f2(P[1][0], P[1][1]), fma2(bc2(T.z2), f2(P[2][0], P[2][1]), bc2(T.pz))));
+}
+// PyBullet Euler triple of the pose (see euler_from_mat): needs R20, R21, R22, R10, R00
+URGYM_HD float3 euler_from_posep(const PoseP &T) {
+    const float sarg = -T.z01.x;
+    if (fabsf(sarg) < 0.99f)
+        return f3(atan2_fast(T.z01.y, T.z2), atan2_fast(sarg, sqrtf(T.z01.y * T.z01.y + T.z2 * T.z2)), atan2_fast(T.c0.y, T.c0.x));
+    const float R[9] = {T.c0.x, T.c1.x, T.c2.x, T.c0.y, T.c1.y, T.c2.y, T.z01.x, T.z01.y, T.z2};
+    return euler_via_quat_ool(R);
 }
 // pose of link `link` (1..6)
 URGYM_HD void fk_link(const ModelConst &M, const float *q, int link, Pose &T) {

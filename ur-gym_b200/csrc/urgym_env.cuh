@@ -368,29 +368,20 @@ URGYM_HD bool robot_pass_rolled(const ModelConst &M, const float *qrow, const Ob
 template <int TASK>
 URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const ObstW &O, bool collide, float *ee,
                                  float *dist, float *cap, int cs) {
-    Pose T;
-    pose_identity(T);
-#ifdef URGYM_FK_ROLLED
-#pragma unroll 1
-#else
+    PoseP T;
+    posep_identity(T);
 #pragma unroll
-#endif
     for (int l = 1; l < 7; l++) {
-#ifdef URGYM_FK_ROLLED
-        const float ql = l == 1 ? q[0] : (l == 2 ? q[1] : (l == 3 ? q[2] : (l == 4 ? q[3] : (l == 5 ? q[4] : q[5]))));
-        fk_advance(M, T, l - 1, ql);
-#else
-        fk_advance(M, T, l - 1, q[l - 1]);
-#endif
+        fkp_advance(M, T, l - 1, q[l - 1]);
         if (collide) {
-            float3 a = T.p + rot(T.R, f3(M.cap_p0[l][0], M.cap_p0[l][1], M.cap_p0[l][2]));
-            float3 b = T.p + rot(T.R, f3(M.cap_p1[l][0], M.cap_p1[l][1], M.cap_p1[l][2]));
+            float2 axy, bxy, abz;
+            capsule_world(M, T, l, axy, bxy, abz);
             float *c = cap + (l - 1) * 6 * cs;
-            c[0] = a.x; c[cs] = a.y; c[2 * cs] = a.z; c[3 * cs] = b.x; c[4 * cs] = b.y; c[5 * cs] = b.z;
+            c[0] = axy.x; c[cs] = axy.y; c[2 * cs] = abz.x; c[3 * cs] = bxy.x; c[4 * cs] = bxy.y; c[5 * cs] = abz.y;
         }
     }
-    float3 e = euler_from_mat(T.R);
-    ee[0] = T.p.x; ee[1] = T.p.y; ee[2] = T.p.z; ee[3] = e.x; ee[4] = e.y; ee[5] = e.z;
+    float3 e = euler_from_posep(T);
+    ee[0] = T.pxy.x; ee[1] = T.pxy.y; ee[2] = T.pz; ee[3] = e.x; ee[4] = e.y; ee[5] = e.z;
     if (!collide) return false;
     bool hit = false;
     // links 2..6 vs obstacle (distances kept: they are get_link_distances' values), table and track

@@ -36,6 +36,14 @@ static void build_model_const(ModelConst &M) {
         for (int k = 0; k < 3; k++) M.joint_xyz[j][k] = (float)UR5E_JOINT_XYZ[3 * j + k];
         for (int k = 0; k < 9; k++) M.joint_rot[j][k] = (float)UR5E_JOINT_ROT[9 * j + k];
     }
+    for (int j = 0; j < 6; j++)
+        for (int k = 0; k < 3; k++)
+            for (int c = 0; c < 3; c++) M.joint_rot_p[j][k][c] = (float)UR5E_JOINT_ROT[9 * j + 3 * k + c];
+    for (int l = 0; l < 7; l++)
+        for (int k = 0; k < 3; k++) {
+            M.cap_pp[l][k][0] = (float)UR5E_CAPSULE_P0[3 * l + k];
+            M.cap_pp[l][k][1] = (float)UR5E_CAPSULE_P1[3 * l + k];
+        }
     const double hull_margin = 0.001;                       // URDF mesh links, Bullet default collision margin
     for (int l = 0; l < 7; l++) {
         for (int k = 0; k < 3; k++) {
