@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--task", default="UR5DynReach-v1")
     ap.add_argument("--envs", type=int, default=1 << 20)
     ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=120, help="untimed steps first: episode ages need ~100 steps to mix")
     ap.add_argument("--geometry", default="capsule")
     ap.add_argument("--tag", default=os.environ.get("URGYM_B200_LIB", "default"))
     a = ap.parse_args()
@@ -26,7 +27,7 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(1234)
     ring = [torch.rand((a.envs, 6), device="cuda", generator=g) * 2 - 1 for _ in range(8)]
     env.reset()
-    for k in range(40):
+    for k in range(a.warmup):
         env.step(ring[k % 8])
     torch.cuda.synchronize()
     env.L.urgym_profile_enable(env.h, 1)

@@ -384,6 +384,7 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
     ee[0] = T.pxy.x; ee[1] = T.pxy.y; ee[2] = T.pz; ee[3] = e.x; ee[4] = e.y; ee[5] = e.z;
     if (!collide) return false;
     bool hit = false;
+    unsigned slow = 0u;
     // links 2..6 vs obstacle (distances kept: they are get_link_distances' values), table and track
     const float3 oa = O.c - M.fit_obst_h * O.u, ob = O.c + M.fit_obst_h * O.u;
 #pragma unroll 1
@@ -396,20 +397,36 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
             hit = hit || (d <= URGYM_COLLISION_MARGIN);
             cap[(36 + l - 2) * cs] = d;
         }
-        // height broad phase per box (table top z = -0.12, track top z = 0): most links stay well above both
-        const float zlow = fminf(a.z, b.z) - (URGYM_COLLISION_MARGIN + m + M.box_margin[0]);
-        if (zlow <= M.box_top) {
-#pragma unroll 1
+        // Table and track (pyb_setup.py:408-417), branch-free for the common cases.  With L the lower end point of
+        // the segment and dz = L.z - (top face of the box core): dz > reach means the whole segment is farther than
+        // `reach` above the box, no hit; otherwise, if L lies over the box's footprint, dist(segment, box) <=
+        // dist(L, box) = max(dz, 0) <= reach, a hit.  Only a low segment whose lower end is beside the footprint
+        // (table edges, most track cases) needs the exact segment-box distance; those are collected in `slow`.
+        {
+            const bool a_low = a.z <= b.z;
+            const float Lx = a_low ? a.x : b.x, Ly = a_low ? a.y : b.y, zmin = fminf(a.z, b.z);
+            const float minx = fminf(a.x, b.x), maxx = fmaxf(a.x, b.x), miny = fminf(a.y, b.y), maxy = fmaxf(a.y, b.y);
+#pragma unroll
             for (int box = 0; box < 2; box++) {
-                if (zlow > M.box_c[box][2] + M.box_he[box][2]) continue;
-                float margin = M.box_margin[box];
-                float reach = URGYM_COLLISION_MARGIN + m + margin;
-                float3 bc = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
-                float3 bh = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
-                if (seg_box_lower2(a, b, bc, bh) <= reach * reach)
-                    hit = hit || (sqrtf(seg_box_dist2(a, b, bc, bh)) - m - margin <= URGYM_COLLISION_MARGIN);
+                const float reach = URGYM_COLLISION_MARGIN + m + M.box_margin[box];
+                const float cx = M.box_c[box][0], cy = M.box_c[box][1], hx = M.box_he[box][0], hy = M.box_he[box][1];
+                const bool near_z = zmin - (M.box_c[box][2] + M.box_he[box][2]) <= reach;
+                const bool over = fabsf(Lx - cx) <= hx && fabsf(Ly - cy) <= hy;
+                const bool beside = maxx >= cx - hx - reach && minx <= cx + hx + reach && maxy >= cy - hy - reach && miny <= cy + hy + reach;
+                hit = hit || (near_z && over);
+                if (near_z && !over && beside) slow |= 1u << (2 * (l - 2) + box);
             }
         }
+    }
+    while (slow) {          // exact segment-box distance for the few (link, box) cases left
+        const int k = __ffs_hd(slow) - 1;
+        slow &= slow - 1u;
+        const int l = 2 + (k >> 1), box = k & 1;
+        const float *c = cap + (l - 1) * 6 * cs;
+        const float3 a = f3(c[0], c[cs], c[2 * cs]), b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
+        const float3 bc = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
+        const float3 bh = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
+        hit = hit || (sqrtf(seg_box_dist2(a, b, bc, bh)) - M.fit_box[l] - M.box_margin[box] <= URGYM_COLLISION_MARGIN);
     }
     // self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6).  Sphere broad phase for all nine with static indices (midpoints and
     // half lengths), then the exact segment-segment test only for the pairs it leaves, in a rolled loop.
