@@ -111,6 +111,9 @@ URGYM_HD float fdiv(float a, float b) {               // division where 2 ulp ar
 
 // ------------------------------------------------------------------------------------------------ constants
 struct alignas(16) ModelConst {
+    // table / track limits per (link, box), precomputed for the branch-free test of robot_pass_capsule:
+    //   [0] zthr = top + reach   [1] cx  [2] cy  [3] hx | [4] hy  [5] xlo = cx - hx - reach  [6] xhi  [7] ylo | [8] yhi
+    float box_lim[7][2][12];
     // packed-math copies (first, so that the pairs sit 8-byte aligned in the constant bank)
     float joint_rot_p[6][3][4]; // rows of joint_rot padded to 4: (F[k][0], F[k][1]) is a constant pair
     float cap_pp[7][3][2];      // (cap_p0[l][k], cap_p1[l][k])
@@ -124,6 +127,8 @@ struct alignas(16) ModelConst {
     float obst_cap_ie;          // 1 / |obstacle capsule segment|^2 (bounding capsule, hull-mode broad phase)
     // capsule geometry proper (urgym_capsule_fit.h): calibrated against the hull geometry
     float fit_obst[7], fit_box[7], fit_self[9];
+    float self_far2[9];         // (2 (margin + fit_self + half lengths))^2: sphere broad phase on DOUBLED midpoints a + b
+    float self_reach2[9];       // (margin + fit_self)^2
     float fit_obst_h, fit_obst_ie;
     float box_top;              // highest top face of the table / track cores (z), for the height broad phase
     int hull_off[8];            // vertex ranges of links 0..6 inside the packed float4 vertex array

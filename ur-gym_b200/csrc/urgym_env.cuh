@@ -408,11 +408,10 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
             const float minx = fminf(a.x, b.x), maxx = fmaxf(a.x, b.x), miny = fminf(a.y, b.y), maxy = fmaxf(a.y, b.y);
 #pragma unroll
             for (int box = 0; box < 2; box++) {
-                const float reach = URGYM_COLLISION_MARGIN + m + M.box_margin[box];
-                const float cx = M.box_c[box][0], cy = M.box_c[box][1], hx = M.box_he[box][0], hy = M.box_he[box][1];
-                const bool near_z = zmin - (M.box_c[box][2] + M.box_he[box][2]) <= reach;
-                const bool over = fabsf(Lx - cx) <= hx && fabsf(Ly - cy) <= hy;
-                const bool beside = maxx >= cx - hx - reach && minx <= cx + hx + reach && maxy >= cy - hy - reach && miny <= cy + hy + reach;
+                const float *L = M.box_lim[l][box];         // zthr, cx, cy, hx, hy, xlo, xhi, ylo, yhi
+                const bool near_z = zmin <= L[0];
+                const bool over = fabsf(Lx - L[1]) <= L[3] && fabsf(Ly - L[2]) <= L[4];
+                const bool beside = maxx >= L[5] && minx <= L[6] && maxy >= L[7] && miny <= L[8];
                 hit = hit || (near_z && over);
                 if (near_z && !over && beside) slow |= 1u << (2 * (l - 2) + box);
             }
@@ -435,7 +434,7 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
 #pragma unroll
         for (int l = 0; l < 6; l++) {
             const float *c = cap + l * 6 * cs;
-            mid[l] = 0.5f * f3(c[0] + c[3 * cs], c[cs] + c[4 * cs], c[2 * cs] + c[5 * cs]);
+            mid[l] = f3(c[0] + c[3 * cs], c[cs] + c[4 * cs], c[2 * cs] + c[5 * cs]);        // a + b: twice the midpoint
         }
         unsigned need = 0u;
 #pragma unroll
@@ -443,8 +442,7 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
             const int l1 = p < 4 ? 1 : (p < 7 ? 2 : 3);
             const int l2 = p < 4 ? p + 3 : (p < 7 ? p : p - 2);
             const float3 dm = mid[l1 - 1] - mid[l2 - 1];
-            const float far = URGYM_COLLISION_MARGIN + M.fit_self[p] + M.cap_hl[l1] + M.cap_hl[l2];
-            if (dot(dm, dm) <= far * far) need |= 1u << p;
+            if (dot(dm, dm) <= M.self_far2[p]) need |= 1u << p;
         }
         while (need) {
             const int p = __ffs_hd(need) - 1;
@@ -454,8 +452,7 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
             const float *c1 = cap + (l1 - 1) * 6 * cs, *c2 = cap + (l2 - 1) * 6 * cs;
             const float3 a1 = f3(c1[0], c1[cs], c1[2 * cs]), b1 = f3(c1[3 * cs], c1[4 * cs], c1[5 * cs]);
             const float3 a2 = f3(c2[0], c2[cs], c2[2 * cs]), b2 = f3(c2[3 * cs], c2[4 * cs], c2[5 * cs]);
-            const float reach = URGYM_COLLISION_MARGIN + M.fit_self[p];
-            hit = hit || (segseg_dist2_fast(a1, b1, a2, b2, M.cap_ia[l1], M.cap_ia[l2]) <= reach * reach);
+            hit = hit || (segseg_dist2_fast(a1, b1, a2, b2, M.cap_ia[l1], M.cap_ia[l2]) <= M.self_reach2[p]);
         }
     }
     if (Traits<TASK>::HAS_OBST) {

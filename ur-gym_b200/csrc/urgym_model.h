@@ -78,6 +78,23 @@ static void build_model_const(ModelConst &M) {
     M.obst_cap_ie = (float)(1.0 / (0.4 * 0.4));
     for (int l = 0; l < 7; l++) { M.fit_obst[l] = (float)URGYM_FIT_OBST[l]; M.fit_box[l] = (float)URGYM_FIT_BOX[l]; }
     for (int k = 0; k < 9; k++) M.fit_self[k] = (float)URGYM_FIT_SELF[k];
+    {
+        const int L1[9] = {1, 1, 1, 1, 2, 2, 2, 3, 3}, L2[9] = {3, 4, 5, 6, 4, 5, 6, 5, 6};
+        for (int p = 0; p < 9; p++) {
+            const float far = 0.01f + M.fit_self[p] + M.cap_hl[L1[p]] + M.cap_hl[L2[p]];    // 0.01 = URGYM_COLLISION_MARGIN
+            const float reach = 0.01f + M.fit_self[p];
+            M.self_far2[p] = 4.0f * far * far;
+            M.self_reach2[p] = reach * reach;
+        }
+    }
+    for (int l = 0; l < 7; l++)
+        for (int b = 0; b < 2; b++) {
+            const float reach = 0.01f + M.fit_box[l] + M.box_margin[b];                 // 0.01 = URGYM_COLLISION_MARGIN
+            const float cx = M.box_c[b][0], cy = M.box_c[b][1], hx = M.box_he[b][0], hy = M.box_he[b][1];
+            float *L = M.box_lim[l][b];
+            L[0] = M.box_c[b][2] + M.box_he[b][2] + reach; L[1] = cx; L[2] = cy; L[3] = hx; L[4] = hy;
+            L[5] = cx - hx - reach; L[6] = cx + hx + reach; L[7] = cy - hy - reach; L[8] = cy + hy + reach;
+        }
     M.fit_obst_h = (float)URGYM_FIT_OBST_H;
     M.fit_obst_ie = (float)(1.0 / (4.0 * URGYM_FIT_OBST_H * URGYM_FIT_OBST_H));
     M.box_top = (float)fmax(tc[2] + th[2] - pm, kc[2] + kh[2] - pm);
