@@ -409,12 +409,33 @@ static URGYM_OOL uint4 philox4x32_10(uint4 c, uint2 k) {
     }
     return c;
 }
+// N independent blocks with their rounds interleaved: a single Philox block is a serial chain of ten dependent
+// multiply rounds, and the auto-reset kernel is bound by exactly that latency (few warps, long dependent chains).
+template <int N> URGYM_HD void philox4x32_10_n(uint4 (&c)[N], uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        if (r) { k.x += 0x9E3779B9u; k.y += 0xBB67AE85u; }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint64_t p0 = (uint64_t)0xD2511F53u * c[i].x, p1 = (uint64_t)0xCD9E8D57u * c[i].z;
+            c[i] = make_uint4((uint32_t)(p1 >> 32) ^ c[i].y ^ k.x, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c[i].w ^ k.y, (uint32_t)p0);
+        }
+    }
+}
 URGYM_HD float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }   // 2^-24
 
 struct ResetStream {        // counter = (iteration*blocks_per_iter + block, episode, env_lo, env_hi); key = seed
     uint2 key; uint32_t episode, env_lo, env_hi, bpi, iter;
     URGYM_HD uint4 block(uint32_t b) const {
         return philox4x32_10(make_uint4(iter * bpi + b, episode, env_lo, env_hi), key);
+    }
+    template <int N> URGYM_HD void blocks(uint32_t b0, uint4 *out) const {      // blocks b0 .. b0 + N - 1, interleaved
+        uint4 c[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) c[i] = make_uint4(iter * bpi + b0 + (uint32_t)i, episode, env_lo, env_hi);
+        philox4x32_10_n<N>(c, key);
+#pragma unroll
+        for (int i = 0; i < N; i++) out[i] = c[i];
     }
 };
 

@@ -391,7 +391,6 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
     for (int l = 2; l < 7; l++) {
         const float *c = cap + (l - 1) * 6 * cs;
         const float3 a = f3(c[0], c[cs], c[2 * cs]), b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
-        const float m = M.fit_box[l];
         if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
             float d = sqrtf(segseg_dist2_fast(a, b, oa, ob, M.cap_ia[l], M.fit_obst_ie)) - M.fit_obst[l];
             hit = hit || (d <= URGYM_COLLISION_MARGIN);
@@ -644,7 +643,7 @@ URGYM_HD bool dyn_pair_far_enough(const ResetStream &rs) {
     float3 olo, ohi;
     obstacle_range<TASK_DYN>(olo, ohi);
     Draws D;
-    D.b[0] = rs.block(0); D.b[1] = rs.block(1);
+    rs.blocks<2>(0, &D.b[0]);
     float dx = lerp_u(olo.x, ohi.x, D.u(3)) - lerp_u(olo.x, ohi.x, D.u(0));
     float dy = lerp_u(olo.y, ohi.y, D.u(4)) - lerp_u(olo.y, ohi.y, D.u(1));
     float dz = lerp_u(olo.z, ohi.z, D.u(5)) - lerp_u(olo.z, ohi.z, D.u(2));
@@ -666,19 +665,19 @@ URGYM_HD int sample_episode(const ModelConst &M, ResetStream rs, float *E, int k
         Draws D;
         bool fail = false;
         if (TASK == TASK_ORI) {                     // slots: goal 0-2, goal_roll 3, goal_yaw 4
-            D.b[0] = rs.block(0); D.b[1] = rs.block(1);
+            rs.blocks<2>(0, &D.b[0]);
             E[0] = lerp_u(glo.x, ghi.x, D.u(0)); E[1] = lerp_u(glo.y, ghi.y, D.u(1)); E[2] = lerp_u(glo.z, ghi.z, D.u(2));
             E[4] = 0.0f;
             euler_constrained(D.u(3), D.u(4), E[3], E[5]);
         } else if (TASK == TASK_OBS) {              // goal 0-2, obstacle 3-5, sign 6, roll 7, pitch 8
-            D.b[0] = rs.block(0); D.b[1] = rs.block(1); D.b[2] = rs.block(2);
+            rs.blocks<3>(0, &D.b[0]);
             E[0] = lerp_u(glo.x, ghi.x, D.u(0)); E[1] = lerp_u(glo.y, ghi.y, D.u(1)); E[2] = lerp_u(glo.z, ghi.z, D.u(2));
             E[3] = lerp_u(olo.x, ohi.x, D.u(3)); E[4] = lerp_u(olo.y, ohi.y, D.u(4)); E[5] = lerp_u(olo.z, ohi.z, D.u(5));
             euler_obstacle(D.u(6), D.u(7), D.u(8), E[6], E[7]);
             E[8] = 0.0f;
             fail = target_obstacle_dist<TASK, GEOM>(M, E, obstacle_static(&E[3])) < 0.1f;        // reach.py:321
         } else if (TASK == TASK_STA) {              // goal 0-2, roll 3, yaw 4, obstacle 5-7, sign 8, roll 9, pitch 10
-            D.b[0] = rs.block(0); D.b[1] = rs.block(1); D.b[2] = rs.block(2);
+            rs.blocks<3>(0, &D.b[0]);
             E[0] = lerp_u(glo.x, ghi.x, D.u(0)); E[1] = lerp_u(glo.y, ghi.y, D.u(1)); E[2] = lerp_u(glo.z, ghi.z, D.u(2));
             E[4] = 0.0f;
             euler_constrained(D.u(3), D.u(4), E[3], E[5]);
@@ -687,13 +686,13 @@ URGYM_HD int sample_episode(const ModelConst &M, ResetStream rs, float *E, int k
             E[11] = 0.0f;
             fail = target_obstacle_dist<TASK, GEOM>(M, E, obstacle_static(&E[6])) < 0.1f;        // reach.py:473
         } else {                                    // Dyn: start 0-2, end 3-5, goal 6-8, roll 9, yaw 10, start s/r/p 11-13, end 14-16
-            D.b[0] = rs.block(0); D.b[1] = rs.block(1);
+            rs.blocks<2>(0, &D.b[0]);
             E[6] = lerp_u(olo.x, ohi.x, D.u(0)); E[7] = lerp_u(olo.y, ohi.y, D.u(1)); E[8] = lerp_u(olo.z, ohi.z, D.u(2));
             E[12] = lerp_u(olo.x, ohi.x, D.u(3)); E[13] = lerp_u(olo.y, ohi.y, D.u(4)); E[14] = lerp_u(olo.z, ohi.z, D.u(5));
             float dx = E[12] - E[6], dy = E[13] - E[7], dz = E[14] - E[8];
             fail = sqrtf(dx * dx + dy * dy + dz * dz) < 1.0f;                                     // reach.py:674-675
             if (!fail || k + 1 >= URGYM_MAX_RESET_ITERS) {      // the other draws matter only for a surviving iteration
-                D.b[2] = rs.block(2); D.b[3] = rs.block(3); D.b[4] = rs.block(4);
+                rs.blocks<3>(2, &D.b[2]);
                 E[0] = lerp_u(glo.x, ghi.x, D.u(6)); E[1] = lerp_u(glo.y, ghi.y, D.u(7)); E[2] = lerp_u(glo.z, ghi.z, D.u(8));
                 E[4] = 0.0f;
                 euler_constrained(D.u(9), D.u(10), E[3], E[5]);

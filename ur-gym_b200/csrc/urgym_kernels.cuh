@@ -285,6 +285,9 @@ struct AuxArgs {
     unsigned *qcount;               // [0] entries, [1] block tickets of the auto-reset kernel
 };
 
+#ifndef URGYM_AUTORESET_BLOCK
+#define URGYM_AUTORESET_BLOCK 32    /* one warp per block: the warps finish at very different times (rejection loops) */
+#endif
 #ifndef URGYM_RESET_GROUP
 #define URGYM_RESET_GROUP 256       /* envs scanned by one warp of the reset kernel: ~11 finished envs at a 4 % done
                                        rate (measured on B200, Dyn 1 Mi envs: 128 -> 0.205, 256 -> 0.199, 512 -> 0.215 ms per step) */
@@ -478,9 +481,9 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_c
 // lanes are dense here: every warp takes 32 queue entries at a time.  The last block to finish empties the queue counter
 // for the next step.
 template <int TASK, int GEOM>
-__global__ void __launch_bounds__(URGYM_BLOCK) urgym_autoreset_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
+__global__ void __launch_bounds__(URGYM_AUTORESET_BLOCK) urgym_autoreset_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
     typedef Traits<TASK> TT;
-    constexpr int D = TT::OBS, W = 32, NW = URGYM_BLOCK / 32;
+    constexpr int D = TT::OBS, W = 32, NW = URGYM_AUTORESET_BLOCK / 32;
     extern __shared__ float4 smem4[];
     float *s_rows_all = reinterpret_cast<float *>(smem4);                    // [NW][32][D] new observation rows
     int *s_list_all = reinterpret_cast<int *>(s_rows_all + NW * W * D);      // [NW][32]
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_autoreset_kernel(const __gr
     }
 }
 template <int TASK, int GEOM> constexpr size_t autoreset_smem_bytes() {
-    return (size_t)URGYM_BLOCK * Traits<TASK>::OBS * sizeof(float) + 2 * URGYM_BLOCK * sizeof(int) +
+    return (size_t)URGYM_AUTORESET_BLOCK * Traits<TASK>::OBS * sizeof(float) + 2 * URGYM_AUTORESET_BLOCK * sizeof(int) +
            (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
 template <int TASK, int GEOM> constexpr size_t reset_smem_bytes() {
@@ -591,14 +594,14 @@ template <int TASK, int GEOM> cudaError_t launch_reset(const ModelConst &M, cons
 }
 template <int TASK, int GEOM> cudaError_t launch_autoreset(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     // enough warps for ~1/8 of the envs finishing in one step; beyond that the warps loop
-    const int64_t blocks = (A.n + 8 * URGYM_BLOCK - 1) / (8 * URGYM_BLOCK);
+    const int64_t blocks = (A.n + 8 * URGYM_AUTORESET_BLOCK - 1) / (8 * URGYM_AUTORESET_BLOCK);
     // Highest launch priority: the kernel is short, latency-bound and sits on the critical path of its chain
     // (step -> auto-reset -> next step), so its blocks should not queue behind the thousands of step-kernel blocks that
     // other chains have in flight.
     static int prio_hi = 1;
     if (prio_hi == 1) { int lo = 0; if (cudaDeviceGetStreamPriorityRange(&lo, &prio_hi) != cudaSuccess) prio_hi = 0; }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(URGYM_BLOCK);
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(URGYM_AUTORESET_BLOCK);
     cfg.dynamicSmemBytes = autoreset_smem_bytes<TASK, GEOM>(); cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributePriority; attr[0].val.priority = prio_hi;
