@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--task", default="UR5DynReach-v1", choices=sorted(OBS_DIM))
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--geometry", default="capsule", choices=["capsule", "hull"])
-    ap.add_argument("--chains", type=int, default=4, help="independent env sub-ranges per GPU in the captured graph (1..8)")
+    ap.add_argument("--chains", type=int, default=8, help="independent env sub-ranges per GPU in the captured graph (1..8)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall-clock budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -185,7 +185,7 @@ def run_ours(args, rank, world, local_rank):
     warm = max(args.warmup, 3)
     for k in range(warm):
         env.step(ring[k % 8])
-    # the timed loop replays a CUDA graph of 8 steps (one per action buffer of the ring): 16 kernels per replay
+    # the timed loop replays a CUDA graph of 8 steps (one per action buffer of the ring): 2 kernels per step and chain
     chains = args.chains if n >= (1 << 19) else 1       # small batches: sub-ranges would not fill the 148 SMs
     graph = env.capture_steps(ring, chains=chains)
     graph.replay()
@@ -221,7 +221,9 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize(dev)
         clock_note = "timed region shorter than the sampler period: sampled during an untimed 0.25 s repeat of the same loop"
     sampler.stop_flag = True
-    launches = 2 * steps                              # step kernel + auto-reset kernel per env step
+    launches = 2 * steps * chains                     # step kernel + auto-reset kernel per env step and chain
+    if rem:
+        launches -= 2 * rem * (chains - 1)            # the eager remainder steps are whole-batch launches
     barrier()
     env.stats(reset=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -267,7 +269,8 @@ def run_ours(args, rank, world, local_rank):
                 "resets_per_step": episodes_per_launch,
                 "whole_step": {"achieved": whole, "frac": whole / peak,
                                "note": "step + auto-reset kernels: (N*B_step + N_done*B_reset) / (timed region / steps)"},
-                "note": "the kernel is bound by the SM issue rate (ncu: ~72 % issue-active, DRAM ~26 %), not by HBM; see DESIGN.md section 5"}
+                "note": "the kernel is bound by the SM issue rate, not by HBM (ncu, steady state: ~77 % issue-active with 75 % of the "
+                        "lanes doing work, DRAM ~37 %); see DESIGN.md section 5 and profiles/"}
 
     # end to end through the host-buffer entry point: pinned host actions in, observations / rewards / flags out
     buf = env.alloc_host_buffers(terminal_obs=False)

@@ -105,7 +105,7 @@ def test_sharding_invariance(ug):
     assert sw["episodes"] > 0 and sw["env_steps"] == n * 40
 
 
-@pytest.mark.parametrize("chains", [2, 3])
+@pytest.mark.parametrize("chains", [2, 3, 8])
 def test_chained_graph_equals_plain_steps(ug, chains):
     """a CUDA graph that advances env sub-ranges as independent chains == the same steps issued one by one"""
     env_id, n, k = "UR5DynReach-v1", 50_000, 6
@@ -151,6 +151,49 @@ def test_fused_autoreset_equals_explicit_reset(ug):
         assert torch.equal(oa["observation"], ob2["observation"])
     for name in ("q", "goal", "obstacle", "link_dist", "elapsed", "ep_return"):
         assert torch.equal(a_env.get_state(name), b_env.get_state(name)), name
+
+
+def test_injected_episode_constants_reach_the_step_kernel(ug):
+    """urgym_set_state of goal / obstacle fields rebuilds the hot planes (episode cache) the step kernel reads:
+    two handles that differ only in HOW they got their episode constants (own reset vs injection) step identically"""
+    for env_id in ("UR5OriReach-v1", "UR5ObsReach-v1", "UR5StaReach-v1", "UR5DynReach-v1"):
+        n = 777
+        a_env = ug.UR5VecEnv(env_id, n, seed=21, auto_reset=False)
+        b_env = ug.UR5VecEnv(env_id, n, seed=99, auto_reset=False)
+        a_env.reset(); b_env.reset()
+        names = ["goal"] + (["obstacle"] if env_id != "UR5OriReach-v1" else []) + (["obstacle_end"] if env_id == "UR5DynReach-v1" else [])
+        for name in names:
+            b_env.set_state(name, a_env.get_state(name))
+        b_env.refresh()
+        if env_id != "UR5OriReach-v1":
+            # (reset takes the neutral pose's capsules from the host's double-precision FK, refresh runs the FP32 chain)
+            assert torch.allclose(a_env.get_state("link_dist"), b_env.get_state("link_dist"), atol=2e-6)
+            b_env.set_state("link_dist", a_env.get_state("link_dist"))
+        g = torch.Generator(device="cuda").manual_seed(5)
+        for t in range(6):
+            act = torch.rand((n, 6), device="cuda", generator=g) * 2 - 1
+            oa, ra, ta, ca, _ = a_env.step(act)
+            ob, rb, tb, cb, _ = b_env.step(act)
+            # the cache words come from two different kernels (reset vs derive): the same formulas, but the compiler
+            # may contract them into FMAs differently, so equality is to round-off, not bitwise
+            assert torch.allclose(oa["observation"], ob["observation"], atol=3e-6, rtol=0), (env_id, t)
+            assert torch.allclose(ra, rb, atol=2e-3, rtol=1e-5) and torch.equal(ta, tb) and torch.equal(ca, cb)
+
+
+def test_kernel_timing_entry_points(ug):
+    """urgym_profile_enable / urgym_profile_read: CUDA events around the step and auto-reset kernels"""
+    env = ug.UR5VecEnv("UR5DynReach-v1", 65536, seed=1)
+    env.reset()
+    act = torch.zeros((65536, 6), device="cuda")
+    assert env.L.urgym_profile_enable(env.h, 1) == 0
+    for _ in range(5):
+        env.step(act)
+    a, b, k = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    assert env.L.urgym_profile_read(env.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(k)) == 0
+    assert k.value == 5 and 0.0 < a.value < 5.0 and 0.0 < b.value < 5.0
+    assert env.L.urgym_profile_enable(env.h, 0) == 0
+    env.step(act)
+    assert env.L.urgym_profile_read(env.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(k)) == 0 and k.value == 0
 
 
 def test_full_size_properties(ug):
