@@ -32,7 +32,7 @@ using namespace urgym;
 #define URGYM_STAT_SLOTS 64
 #define URGYM_RETURN_SCALE 65536.0f     /* episode returns are summed in 2^-16 fixed point: order-independent */
 
-// The model constants (~1.3 KB) travel as a __grid_constant__ kernel parameter: they sit in the constant bank like
+// The model constants (~3 KB) travel as a __grid_constant__ kernel parameter: they sit in the constant bank like
 // __constant__ data would, without a global symbol shared between translation units.
 
 // ------------------------------------------------------------------------------------------------ state planes
@@ -384,22 +384,20 @@ __device__ __forceinline__ unsigned long long reset_listed(const ModelConst &c_m
             store_hot<TASK>(A.st, i, s);
         }
         __syncwarp();
-        // new rows -> global: every lane writes its own row (the rows of reset envs are scattered anyway)
-        if (j < cnt) {
-            const int64_t i = gbase + s_list[j];
-            const float *row = s_rows + lane * D;
+        // new rows -> global, one row per iteration with the lanes along the row: a lane writing its own row would put
+        // 32 different sectors into every store instruction (the memory pipeline throttled on exactly that)
+        const int nrows = min(W, cnt - j0);
+#pragma unroll 4
+        for (int r = 0; r < nrows; r++) {
+            const int64_t i = gbase + s_list[j0 + r];
+            const float *row = s_rows + r * D;
             if (A.obs) {
-#pragma unroll
-                for (int c = 0; c < D; c++) A.obs[i * D + c] = row[c];
+                float *g = A.obs + i * D;
+                if (lane < D) g[lane] = row[lane];
+                if (lane + W < D) g[lane + W] = row[lane + W];
             }
-            if (A.ach) {
-#pragma unroll
-                for (int c = 0; c < G; c++) A.ach[i * G + c] = row[c];
-            }
-            if (A.des) {
-#pragma unroll
-                for (int c = 0; c < G; c++) A.des[i * G + c] = row[12 + c];
-            }
+            if (A.ach && lane < G) A.ach[i * G + lane] = row[lane];
+            if (A.des && lane < G) A.des[i * G + lane] = row[12 + lane];
         }
         __syncwarp();
     }
