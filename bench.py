@@ -35,7 +35,8 @@ def parse():
     ap.add_argument("--task", default="UR5DynReach-v1", choices=sorted(OBS_DIM))
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--geometry", default="capsule", choices=["capsule", "hull"])
-    ap.add_argument("--chains", type=int, default=8, help="independent env sub-ranges per GPU in the captured graph (1..8)")
+    ap.add_argument("--chains", type=int, default=4, help="independent env sub-ranges per GPU in the captured graph (1..8)")
+    ap.add_argument("--graph-steps", type=int, default=32, help="env steps captured per CUDA graph replay (multiple of 8)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall-clock budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -47,6 +48,7 @@ def workload_config(args, world):
                         f"auto-reset on, {args.geometry} geometry",
             "task": args.task, "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
             "geometry": args.geometry, "chains_per_gpu": args.chains if args.envs_per_gpu >= (1 << 19) else 1, "sharding": f"env index ranges over {world} rank(s), no data-path collective",
+            "graph_steps": max(8, args.graph_steps // 8 * 8),
             "l2": "per-step traffic (state + actions + outputs) exceeds the 126 MB L2; an 8-deep ring of action buffers"}
 
 
@@ -187,11 +189,12 @@ def run_ours(args, rank, world, local_rank):
         env.step(ring[k % 8])
     # the timed loop replays a CUDA graph of 8 steps (one per action buffer of the ring): 2 kernels per step and chain
     chains = args.chains if n >= (1 << 19) else 1       # small batches: sub-ranges would not fill the 148 SMs
-    graph = env.capture_steps(ring, chains=chains)
+    gs = max(8, args.graph_steps // 8 * 8)
+    graph = env.capture_steps(ring * (gs // 8), chains=chains)
     graph.replay()
     env.stats(reset=True)
     steps = max(args.steps, 1)
-    n_replays, rem = divmod(steps, 8)                 # exactly `steps` env steps: whole replays + eager remainder
+    n_replays, rem = divmod(steps, gs)                # exactly `steps` env steps: whole replays + eager remainder
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -207,7 +210,7 @@ def run_ours(args, rank, world, local_rank):
     for k in range(n_replays):
         graph.replay()
     for k in range(rem):
-        env.step(ring[k])
+        env.step(ring[k % 8])
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
