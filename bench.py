@@ -176,7 +176,13 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the simulator has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout; the contract is ONE JSON line there, so everything but the final
+        # print goes to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     n = args.envs_per_gpu
     env = ug.UR5VecEnv(args.task, n, device=local_rank, seed=0, env_index_offset=rank * n, geometry=args.geometry,
@@ -306,6 +312,9 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
                                     "sample": f"{procs} processes x {per_proc} env steps of {args.task} on the oracle port "
                                               f"({cdt:.1f} s wall); PyBullet itself is not installable here"}
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
