@@ -127,7 +127,7 @@ struct alignas(16) ModelConst {
     float obst_cap_ie;          // 1 / |obstacle capsule segment|^2 (bounding capsule, hull-mode broad phase)
     // capsule geometry proper (urgym_capsule_fit.h): calibrated against the hull geometry
     float fit_obst[7], fit_box[7], fit_self[9];
-    float self_far2[9];         // (2 (margin + fit_self + half lengths))^2: sphere broad phase on DOUBLED midpoints a + b
+    float self_far2[9];         // squared broad-phase thresholds of the self pairs (urgym_model.h)
     float self_reach2[9];       // (margin + fit_self)^2
     float fit_obst_h, fit_obst_ie;
     float box_top;              // highest top face of the table / track cores (z), for the height broad phase

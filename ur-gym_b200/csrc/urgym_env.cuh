@@ -429,19 +429,37 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
     // self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6).  Sphere broad phase for all nine with static indices (midpoints and
     // half lengths), then the exact segment-segment test only for the pairs it leaves, in a rolled loop.
     {
-        float3 mid[6];
+        // Broad phase.  Every pair has a short member (links 1, 4, 5, 6: capsule half lengths 2..34 mm), contained
+        // in the ball of that radius about its midpoint, so  dist(pair) >= dist(midpoint, other segment) - half length.
+        // For the pairs with a long member (upper arm 2, forearm 3) that point-segment bound is far tighter than the
+        // sphere-sphere bound: in steady state the spheres let 100 % of the (3,5) and 28 % of the (3,6) pairs through
+        // (1.4 exact tests per env, 3.6 for the slowest lane of a warp), the point-segment bound ~1 % in total.
+        // (1,4) (1,5) (1,6) keep the sphere test (both members short).
+        float3 mid[6], sa[2], sd[2];        // midpoints of links 1, 4, 5, 6 (index l - 1); a and b - a of links 2, 3
 #pragma unroll
         for (int l = 0; l < 6; l++) {
             const float *c = cap + l * 6 * cs;
-            mid[l] = f3(c[0] + c[3 * cs], c[cs] + c[4 * cs], c[2 * cs] + c[5 * cs]);        // a + b: twice the midpoint
+            const float3 a = f3(c[0], c[cs], c[2 * cs]), b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
+            if (l == 1 || l == 2) { sa[l - 1] = a; sd[l - 1] = b - a; }
+            else mid[l] = 0.5f * (a + b);
         }
         unsigned need = 0u;
 #pragma unroll
         for (int p = 0; p < 9; p++) {
             const int l1 = p < 4 ? 1 : (p < 7 ? 2 : 3);
             const int l2 = p < 4 ? p + 3 : (p < 7 ? p : p - 2);
-            const float3 dm = mid[l1 - 1] - mid[l2 - 1];
-            if (dot(dm, dm) <= M.self_far2[p]) need |= 1u << p;
+            float d2;
+            if (l1 == 1 && l2 != 3) {                       // short - short: sphere test
+                const float3 dm = mid[0] - mid[l2 - 1];
+                d2 = dot(dm, dm);
+            } else {                                        // midpoint of the short member vs the long member's segment
+                const int ll = (l1 == 1) ? 3 : l1, ls = (l1 == 1) ? 1 : l2;
+                const float3 ap = mid[ls - 1] - sa[ll - 2];
+                const float t = clampf(dot(ap, sd[ll - 2]) * M.cap_ia[ll], 0.0f, 1.0f);
+                const float3 e = ap - t * sd[ll - 2];
+                d2 = dot(e, e);
+            }
+            if (d2 <= M.self_far2[p]) need |= 1u << p;
         }
         while (need) {
             const int p = __ffs_hd(need) - 1;

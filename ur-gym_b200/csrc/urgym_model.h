@@ -81,9 +81,13 @@ static void build_model_const(ModelConst &M) {
     {
         const int L1[9] = {1, 1, 1, 1, 2, 2, 2, 3, 3}, L2[9] = {3, 4, 5, 6, 4, 5, 6, 5, 6};
         for (int p = 0; p < 9; p++) {
-            const float far = 0.01f + M.fit_self[p] + M.cap_hl[L1[p]] + M.cap_hl[L2[p]];    // 0.01 = URGYM_COLLISION_MARGIN
-            const float reach = 0.01f + M.fit_self[p];
-            M.self_far2[p] = 4.0f * far * far;
+            // broad-phase threshold: midpoint-midpoint for the short-short pairs (1,4) (1,5) (1,6), midpoint of the short
+            // member against the long member's segment for the others (robot_pass_capsule)
+            const bool spheres = L1[p] == 1 && L2[p] != 3;
+            const int ls = L1[p] == 1 ? 1 : L2[p];
+            const float reach = 0.01f + M.fit_self[p];                                       // 0.01 = URGYM_COLLISION_MARGIN
+            const float far = spheres ? reach + M.cap_hl[L1[p]] + M.cap_hl[L2[p]] : reach + M.cap_hl[ls];
+            M.self_far2[p] = far * far;
             M.self_reach2[p] = reach * reach;
         }
     }
