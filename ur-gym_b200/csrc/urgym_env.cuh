@@ -426,8 +426,8 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
         const float3 bh = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
         hit = hit || (sqrtf(seg_box_dist2(a, b, bc, bh)) - M.fit_box[l] - M.box_margin[box] <= URGYM_COLLISION_MARGIN);
     }
-    // self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6).  Sphere broad phase for all nine with static indices (midpoints and
-    // half lengths), then the exact segment-segment test only for the pairs it leaves, in a rolled loop.
+    // self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6), pair index p = 0..8 in that order: a broad phase for all nine with static
+    // indices, then the exact segment-segment test only for the pairs it leaves, in a rolled loop.
     {
         // Broad phase.  Every pair has a short member (links 1, 4, 5, 6: capsule half lengths 2..34 mm), contained
         // in the ball of that radius about its midpoint, so  dist(pair) >= dist(midpoint, other segment) - half length.
