@@ -687,6 +687,18 @@ URGYM_HD float segseg_dist2_fast(float3 p1, float3 q1, float3 p2, float3 q2, flo
     float3 dd = (r + s * d1) - t * d2;
     return dot(dd, dd);
 }
+// squared distance between the link segment a-b and the obstacle's axis segment (centre c, UNIT axis u, half length h):
+// segseg_dist2_fast with the second segment parametrised by arc length about its centre (e = 1, no division by it)
+URGYM_HD float seg_axis_dist2(float3 a, float3 b, float3 c, float3 u, float h, float inv_a) {
+    const float3 d1 = b - a, r = a - c;
+    const float A = dot(d1, d1), B = dot(d1, u), C = dot(d1, r), F = dot(u, r);
+    const float denom = fmaf(-B, B, A);
+    float s = denom > 1e-12f * A ? clampf(fdiv(fmaf(B, F, -C), denom), 0.0f, 1.0f) : 0.0f;
+    const float t = clampf(fmaf(B, s, F), -h, h);
+    s = clampf(fmaf(B, t, -C) * inv_a, 0.0f, 1.0f);
+    const float3 dd = (r + s * d1) - t * u;
+    return dot(dd, dd);
+}
 URGYM_HD float seg_box_lower2(float3 a, float3 b, float3 c, float3 he) {
     float gx = fmaxf(fmaxf(fminf(a.x, b.x) - (c.x + he.x), (c.x - he.x) - fmaxf(a.x, b.x)), 0.0f);
     float gy = fmaxf(fmaxf(fminf(a.y, b.y) - (c.y + he.y), (c.y - he.y) - fmaxf(a.y, b.y)), 0.0f);

@@ -386,13 +386,12 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
     bool hit = false;
     unsigned slow = 0u;
     // links 2..6 vs obstacle (distances kept: they are get_link_distances' values), table and track
-    const float3 oa = O.c - M.fit_obst_h * O.u, ob = O.c + M.fit_obst_h * O.u;
 #pragma unroll 1
     for (int l = 2; l < 7; l++) {
         const float *c = cap + (l - 1) * 6 * cs;
         const float3 a = f3(c[0], c[cs], c[2 * cs]), b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
         if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
-            float d = sqrtf(segseg_dist2_fast(a, b, oa, ob, M.cap_ia[l], M.fit_obst_ie)) - M.fit_obst[l];
+            float d = sqrtf(seg_axis_dist2(a, b, O.c, O.u, M.fit_obst_h, M.cap_ia[l])) - M.fit_obst[l];
             hit = hit || (d <= URGYM_COLLISION_MARGIN);
             cap[(36 + l - 2) * cs] = d;
         }
