@@ -196,6 +196,42 @@ def test_kernel_timing_entry_points(ug):
     assert env.L.urgym_profile_read(env.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(k)) == 0 and k.value == 0
 
 
+def test_sta_4mi_envs_sharded_properties(ug):
+    """BASELINE config C4's size: UR5StaReach-v1, 4 Mi envs, here as two shards of 2 Mi on one GPU.  Size-independent
+    properties: sampling boxes, target-obstacle rejection rule, determinism of a shard against the same shard re-run,
+    statistics additive and equal to a torch-side recount."""
+    env_id, n_shard = "UR5StaReach-v1", 1 << 21
+    shards = [ug.UR5VecEnv(env_id, n_shard, seed=77, env_index_offset=k * n_shard) for k in range(2)]
+    again = ug.UR5VecEnv(env_id, n_shard, seed=77, env_index_offset=n_shard)
+    for e in shards + [again]:
+        e.reset()
+    lo, hi = torch.tensor([0.3, -0.5, 0.0], device="cuda"), torch.tensor([0.75, 0.5, 0.2], device="cuda")
+    olo, ohi = torch.tensor([0.5, -0.5, 0.25], device="cuda"), torch.tensor([1.0, 0.5, 0.55], device="cuda")
+    for e in shards:
+        goal, obst = e.get_state("goal"), e.get_state("obstacle")
+        assert ((goal[:, :3] >= lo) & (goal[:, :3] <= hi)).all()                    # reach.py:385-386
+        assert ((obst[:, :3] >= olo) & (obst[:, :3] <= ohi)).all()                  # reach.py:387-388
+        # rejection rule (reach.py:473): the capsule stand-in keeps target and obstacle axis farther apart than
+        # 0.1 + the two radii minus the obstacle's half length along its axis
+        assert ((goal[:, :3] - obst[:, :3]).norm(dim=1) > 0.1).all()
+    assert not torch.equal(shards[0].get_state("goal"), shards[1].get_state("goal"))
+    g = torch.Generator(device="cuda").manual_seed(11)
+    done_count, succ_count = [0, 0], [0, 0]
+    for t in range(12):
+        act = torch.rand((n_shard, 6), device="cuda", generator=g) * 2 - 1
+        for k, e in enumerate(shards):
+            obs, rew, term, trunc, info = e.step(act)
+            assert torch.isfinite(rew).all()
+            done_count[k] += int((term | trunc).sum()); succ_count[k] += int(info["is_success"].sum())
+        o2, r2, t2, c2, _ = again.step(act)
+        assert torch.equal(o2["observation"], shards[1].obs) and torch.equal(r2, shards[1].reward) and torch.equal(t2, shards[1].terminated)
+    st = [e.stats() for e in shards]
+    for k in range(2):
+        assert st[k]["episodes"] == done_count[k] and st[k]["successes"] == succ_count[k]
+        assert st[k]["env_steps"] == 12 * n_shard
+    assert sum(s["episodes"] for s in st) > 0
+
+
 def test_full_size_properties(ug):
     """BASELINE config: UR5DynReach-v1, 1 Mi envs on one GPU.  Size-independent properties."""
     env_id, n, steps = "UR5DynReach-v1", 1 << 20, 120
