@@ -21,17 +21,14 @@ struct FieldArgs {
 };
 
 __device__ __forceinline__ float *e_word(const StateView &st, int task, int64_t i, int w) {
-    const int EW = task == TASK_ORI ? 6 : (task == TASK_OBS ? 9 : (task == TASK_STA ? 12 : 18));
-    const int NF = EW / 4;
-    if (w < 4 * NF) return reinterpret_cast<float *>(&st.e4[w / 4][i]) + (w % 4);
-    if (EW % 4 == 2) return reinterpret_cast<float *>(&st.e2[i]) + (w - 4 * NF);
-    return &st.e1[i];
+    (void)task;         // word w of E: 32-byte group w / 8, float4 (w % 8) / 4 of the env's pair, component w % 4
+    return reinterpret_cast<float *>(&st.e8[w / 8][2 * i + (w % 8) / 4]) + (w % 4);
 }
 
 __global__ void __launch_bounds__(URGYM_BLOCK) urgym_field_kernel(const FieldArgs A) {
     const int64_t i = (int64_t)blockIdx.x * URGYM_BLOCK + threadIdx.x;
     if (i >= A.n) return;
-    float *qa = reinterpret_cast<float *>(&A.st.qa[i]), *qb = reinterpret_cast<float *>(&A.st.qb[i]);
+    float *qa = reinterpret_cast<float *>(&A.st.q8[2 * i]), *qb = reinterpret_cast<float *>(&A.st.q8[2 * i + 1]);
     float *x = reinterpret_cast<float *>(A.ext);
     auto mv = [&](float *plane, float *e) { if (A.to_state) *plane = *e; else *e = *plane; };
     switch (A.field) {
@@ -61,7 +58,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_field_kernel(const FieldArg
         break;
     }
     case URGYM_F_VELOCITY: {
-        float *a = reinterpret_cast<float *>(&A.st.va[i]), *b = reinterpret_cast<float *>(&A.st.vb[i]);
+        float *a = reinterpret_cast<float *>(&A.st.v8[2 * i]), *b = reinterpret_cast<float *>(&A.st.v8[2 * i + 1]);
         for (int k = 0; k < 4; k++) mv(a + k, x + i * 6 + k);
         for (int k = 0; k < 2; k++) mv(b + k, x + i * 6 + 4 + k);
         break;
@@ -174,24 +171,18 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
         build_model_const(h->model);
         // planes: 16-byte groups first, all 256-byte aligned
         const size_t n = (size_t)n_envs;
-        const size_t p16 = align_up(n * 16, 256), p8 = align_up(n * 8, 256), p4 = align_up(n * 4, 256);
-        const size_t total = 3 * p16 + p4 + 4 * p16 + p8 + p4 + p16 + p8 + 5 * p16 + p8 + p4 + p4 +
+        const size_t p32 = align_up(n * 32, 256), p16 = align_up(n * 16, 256), p4 = align_up(n * 4, 256);
+        const size_t total = p32 + p16 + p4 + 3 * p32 + p32 + 3 * p32 + p4 +
                              URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8 + 256 + 256;
         if ((e = cudaMalloc(&h->pool, total)) != cudaSuccess) { rc = URGYM_ENOMEM; break; }
         if ((e = cudaMemset(h->pool, 0, total)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
         char *p = (char *)h->pool;
-        h->st.qa = (float4 *)p; p += p16;
-        h->st.qb = (float4 *)p; p += p16;
+        h->st.q8 = (float4 *)p; p += p32;
         h->st.ld4 = (float4 *)p; p += p16;
         h->st.ld1 = (float *)p; p += p4;
-        for (int g = 0; g < 4; g++) { h->st.e4[g] = (float4 *)p; p += p16; }
-        h->st.e2 = (float2 *)p; p += p8;
-        h->st.e1 = (float *)p; p += p4;
-        h->st.va = (float4 *)p; p += p16;
-        h->st.vb = (float2 *)p; p += p8;
-        for (int g = 0; g < 5; g++) { h->st.h4[g] = (float4 *)p; p += p16; }
-        h->st.h2 = (float2 *)p; p += p8;
-        h->st.h1 = (float *)p; p += p4;
+        for (int g = 0; g < 3; g++) { h->st.e8[g] = (float4 *)p; p += p32; }
+        h->st.v8 = (float4 *)p; p += p32;
+        for (int g = 0; g < 3; g++) { h->st.h8[g] = (float4 *)p; p += p32; }
         h->queue = (int *)p; p += p4;
         h->stats = (unsigned long long *)p; p += URGYM_STAT_SLOTS * URGYM_STATS_COUNT * 8;
         h->d_event = (uint32_t *)p; p += 256;
@@ -276,11 +267,8 @@ extern "C" int urgym_set_event(urgym_env_t *h, uint32_t event) {
 
 static StateView view_at(const StateView &v, int64_t off) {
     StateView o = v;
-    o.qa += off; o.qb += off; o.ld4 += off; o.ld1 += off;
-    for (int g = 0; g < 4; g++) o.e4[g] += off;
-    o.e2 += off; o.e1 += off; o.va += off; o.vb += off;
-    for (int g = 0; g < 5; g++) o.h4[g] += off;
-    o.h2 += off; o.h1 += off;
+    o.q8 += 2 * off; o.ld4 += off; o.ld1 += off; o.v8 += 2 * off;
+    for (int g = 0; g < 3; g++) { o.e8[g] += 2 * off; o.h8[g] += 2 * off; }
     return o;
 }
 

@@ -1,19 +1,18 @@
 // urgym_kernels.cuh -- sm_100a kernels of the batched UR5e reach simulator (C ABI: urgym_api.cu).
 //
-// Layout in HBM (per handle, one cudaMalloc): structure-of-arrays planes of 16-byte groups, one env per thread,
-// so a warp reads/writes 512 contiguous bytes per plane:
-//   qa  float4[N]  q0..q3                           rw every step
-//   qb  float4[N]  q4, q5, elapsed (int bits), episode return       rw every step
-//   ld4 float4[N]  link_dist 0..3 ; ld1 float[N] link_dist 4        rw every step (not Ori)
-//   e4[g] float4[N], e2 float2[N] / e1 float[N]   episode constants E (goal, obstacle poses): read every step,
-//                                                   written only at reset
-//   va float4[N], vb float2[N]                      ReachDyn.velocity as left by the previous episode (quirk Q4)
+// Layout in HBM (per handle, one cudaMalloc): structure-of-arrays planes, one env per thread; the planes that a reset
+// rewrites env by env are 32-byte groups (one 256-bit access per lane, 1 KB of contiguous memory per warp and group):
+//   q8  [2N] float4  q0..q3 | q4, q5, elapsed (int bits), episode return        rw every step
+//   ld4 [N] float4, ld1 [N] float   link_dist = last_dist                         rw every step (not Ori)
+//   h8[g] [2N] float4  hot words: the episode constants the step reads + the episode cache   read every step
+//   e8[g] [2N] float4  episode constants E as the reference holds them             cold (reset, state access)
+//   v8  [2N] float4  ReachDyn.velocity as left by the previous episode (quirk Q4)   reset only
 // Caller-facing arrays (actions [N,6], obs [N,D], achieved [N,G]) are row-major as the reference's numpy arrays
-// are; a block stages its 128-row tile in shared memory so that global traffic is 16-byte vectorised and coalesced.
+// are; a warp stages its 32 observation rows in shared memory so that they leave as 16-byte coalesced stores.
 //
-// The step kernel is one fused pass: action -> joints -> obstacle motion -> FK -> collision / link distances ->
-// observation -> success / reward / TimeLimit -> statistics -> terminal observation -> auto-reset of finished envs
-// (done lanes are compacted with a warp ballot so that the rejection-sampling loop runs in dense warps).
+// Per env step two kernels: urgym_step_kernel (action -> joints -> obstacle motion -> FK -> collision / link distances
+// -> observation -> success / reward / TimeLimit -> statistics -> terminal rows, finished envs appended to a queue)
+// and urgym_autoreset_kernel (the queued envs, dense: 32 per warp, one per lane).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,42 +35,54 @@ using namespace urgym;
 // __constant__ data would, without a global symbol shared between translation units.
 
 // ------------------------------------------------------------------------------------------------ state planes
+// Planes that the auto-reset kernel writes env by env are kept in 32-BYTE groups per env (two float4), so that a reset
+// writes whole 32-byte sectors: the ECC-protected HBM can only write a partial sector by read-modify-write, and 18
+// partial stores per reset were what that kernel spent its time waiting for.  A warp of the step kernel still moves
+// 1 KB of contiguous memory per group.
 struct StateView {
-    float4 *qa, *qb, *ld4;
-    float *ld1;
-    float4 *e4[4];
-    float2 *e2;
-    float *e1;
-    float4 *va;
-    float2 *vb;
-    // hot planes: the words of E the step reads plus the episode cache C (urgym_env.cuh, Traits::EH / CW), written at
-    // reset (and after a state injection), read by every step instead of e4/e2/e1
-    float4 *h4[5];
-    float2 *h2;
-    float *h1;
+    float4 *q8;             // [2N]  q0..q3 | q4, q5, elapsed (int bits), episode return
+    float4 *ld4;            // [N]   link_dist 0..3
+    float *ld1;             // [N]   link_dist 4
+    float4 *e8[3];          // [2N]  episode constants E, 8 words per group
+    float4 *v8;             // [2N]  ReachDyn.velocity carried over a reset (6 words)
+    float4 *h8[3];          // [2N]  hot words H = E[0..EH) ++ C, 8 words per group
 };
 
+// One 256-bit access per 32-byte group (LDG.E.256 / STG.E.256, new with sm_100): a warp reads or writes 1 KB of
+// contiguous memory per instruction.  p points at the env's pair of float4 (32-byte aligned).
+__device__ __forceinline__ void ld_group(const float4 *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void st_group(float4 *p, float4 a, float4 b) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+                 "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+}
 template <int TASK> __device__ __forceinline__ void load_E(const StateView &st, int64_t i, float *E) {
-    constexpr int EW = Traits<TASK>::EW, NF = EW / 4, TAIL = EW % 4;
+    constexpr int EW = Traits<TASK>::EW;
 #pragma unroll
-    for (int g = 0; g < NF; g++) {
-        float4 v = st.e4[g][i];
-        E[4 * g] = v.x; E[4 * g + 1] = v.y; E[4 * g + 2] = v.z; E[4 * g + 3] = v.w;
+    for (int g = 0; 4 * g < EW; g++) {
+        const float4 v = st.e8[g >> 1][2 * i + (g & 1)];
+        E[4 * g] = v.x;
+        if (4 * g + 1 < EW) E[4 * g + 1] = v.y;
+        if (4 * g + 2 < EW) E[4 * g + 2] = v.z;
+        if (4 * g + 3 < EW) E[4 * g + 3] = v.w;
     }
-    if (TAIL == 2) { float2 v = st.e2[i]; E[4 * NF] = v.x; E[4 * NF + 1] = v.y; }
-    if (TAIL == 1) { E[4 * NF] = st.e1[i]; }
 }
 template <int TASK> __device__ __forceinline__ void store_E(const StateView &st, int64_t i, const float *E) {
-    constexpr int EW = Traits<TASK>::EW, NF = EW / 4, TAIL = EW % 4;
+    constexpr int EW = Traits<TASK>::EW, NG = (EW + 7) / 8;      // whole 32-byte groups are written (padding: zeros)
 #pragma unroll
-    for (int g = 0; g < NF; g++) st.e4[g][i] = make_float4(E[4 * g], E[4 * g + 1], E[4 * g + 2], E[4 * g + 3]);
-    if (TAIL == 2) st.e2[i] = make_float2(E[4 * NF], E[4 * NF + 1]);
-    if (TAIL == 1) st.e1[i] = E[4 * NF];
+    for (int G = 0; G < NG; G++) {
+        auto w = [&](int k) { return 8 * G + k < EW ? E[8 * G + k] : 0.0f; };
+        st_group(st.e8[G] + 2 * i, make_float4(w(0), w(1), w(2), w(3)), make_float4(w(4), w(5), w(6), w(7)));
+    }
 }
-// hot words H = E[0..EH) ++ C[0..CW): HW/4 float4 planes, then a float2 and/or a float plane for the tail
+// hot words H = E[0..EH) ++ C[0..CW)
 template <int TASK> struct HotLayout {
-    static constexpr int EH = Traits<TASK>::EH, CW = Traits<TASK>::CW, HW = EH + CW, NF = HW / 4, TAIL = HW % 4;
-    static_assert(NF <= 5, "hot planes");
+    static constexpr int EH = Traits<TASK>::EH, CW = Traits<TASK>::CW, HW = EH + CW, NG = (HW + 7) / 8;
+    static_assert(NG <= 3, "hot planes");
 };
 template <int TASK> __device__ __forceinline__ float &hot_word(EnvState &s, int w) {
     return w < HotLayout<TASK>::EH ? s.E[w] : s.C[w - HotLayout<TASK>::EH];
@@ -79,25 +90,37 @@ template <int TASK> __device__ __forceinline__ float &hot_word(EnvState &s, int 
 template <int TASK> __device__ __forceinline__ void load_hot(const StateView &st, int64_t i, EnvState &s) {
     typedef HotLayout<TASK> L;
 #pragma unroll
-    for (int g = 0; g < L::NF; g++) {
-        const float4 v = st.h4[g][i];
-        hot_word<TASK>(s, 4 * g) = v.x; hot_word<TASK>(s, 4 * g + 1) = v.y; hot_word<TASK>(s, 4 * g + 2) = v.z; hot_word<TASK>(s, 4 * g + 3) = v.w;
+    for (int G = 0; G < L::NG; G++) {
+        float4 v[2];
+        ld_group(st.h8[G] + 2 * i, v[0], v[1]);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int w = 8 * G + 4 * h;
+            if (w < L::HW) hot_word<TASK>(s, w) = v[h].x;
+            if (w + 1 < L::HW) hot_word<TASK>(s, w + 1) = v[h].y;
+            if (w + 2 < L::HW) hot_word<TASK>(s, w + 2) = v[h].z;
+            if (w + 3 < L::HW) hot_word<TASK>(s, w + 3) = v[h].w;
+        }
     }
-    if (L::TAIL >= 2) { const float2 v = st.h2[i]; hot_word<TASK>(s, 4 * L::NF) = v.x; hot_word<TASK>(s, 4 * L::NF + 1) = v.y; }
-    if (L::TAIL == 1) hot_word<TASK>(s, 4 * L::NF) = st.h1[i];
-    if (L::TAIL == 3) hot_word<TASK>(s, 4 * L::NF + 2) = st.h1[i];
 }
 template <int TASK> __device__ __forceinline__ void store_hot(const StateView &st, int64_t i, EnvState &s) {
     typedef HotLayout<TASK> L;
 #pragma unroll
-    for (int g = 0; g < L::NF; g++)
-        st.h4[g][i] = make_float4(hot_word<TASK>(s, 4 * g), hot_word<TASK>(s, 4 * g + 1), hot_word<TASK>(s, 4 * g + 2), hot_word<TASK>(s, 4 * g + 3));
-    if (L::TAIL >= 2) st.h2[i] = make_float2(hot_word<TASK>(s, 4 * L::NF), hot_word<TASK>(s, 4 * L::NF + 1));
-    if (L::TAIL == 1) st.h1[i] = hot_word<TASK>(s, 4 * L::NF);
-    if (L::TAIL == 3) st.h1[i] = hot_word<TASK>(s, 4 * L::NF + 2);
+    for (int G = 0; G < L::NG; G++) {
+        auto w = [&](int k) { return 8 * G + k < L::HW ? hot_word<TASK>(s, 8 * G + k) : 0.0f; };
+        st_group(st.h8[G] + 2 * i, make_float4(w(0), w(1), w(2), w(3)), make_float4(w(4), w(5), w(6), w(7)));
+    }
+}
+__device__ __forceinline__ void load_vel(const StateView &st, int64_t i, float *vel) {
+    const float4 a = st.v8[2 * i], b = st.v8[2 * i + 1];
+    vel[0] = a.x; vel[1] = a.y; vel[2] = a.z; vel[3] = a.w; vel[4] = b.x; vel[5] = b.y;
+}
+__device__ __forceinline__ void store_vel(const StateView &st, int64_t i, const float *vel) {
+    st_group(st.v8 + 2 * i, make_float4(vel[0], vel[1], vel[2], vel[3]), make_float4(vel[4], vel[5], 0.0f, 0.0f));
 }
 template <int TASK> __device__ __forceinline__ void load_dyn(const StateView &st, int64_t i, EnvState &s) {
-    float4 a = st.qa[i], b = st.qb[i];
+    float4 a, b;
+    ld_group(st.q8 + 2 * i, a, b);
     s.q[0] = a.x; s.q[1] = a.y; s.q[2] = a.z; s.q[3] = a.w; s.q[4] = b.x; s.q[5] = b.y;
     s.elapsed = __float_as_int(b.z);
     s.ep_ret = b.w;
@@ -110,8 +133,8 @@ template <int TASK> __device__ __forceinline__ void load_dyn(const StateView &st
     }
 }
 template <int TASK> __device__ __forceinline__ void store_dyn(const StateView &st, int64_t i, const EnvState &s) {
-    st.qa[i] = make_float4(s.q[0], s.q[1], s.q[2], s.q[3]);
-    st.qb[i] = make_float4(s.q[4], s.q[5], __int_as_float(s.elapsed), s.ep_ret);
+    st_group(st.q8 + 2 * i, make_float4(s.q[0], s.q[1], s.q[2], s.q[3]),
+             make_float4(s.q[4], s.q[5], __int_as_float(s.elapsed), s.ep_ret));
     if (Traits<TASK>::HAS_OBST) {
         st.ld4[i] = make_float4(s.ld[0], s.ld[1], s.ld[2], s.ld[3]);
         st.ld1[i] = s.ld[4];
@@ -363,15 +386,13 @@ __device__ __forceinline__ unsigned long long reset_listed(const ModelConst &c_m
                     load_dyn<TASK>(A.st, i, s);
                     load_hot<TASK>(A.st, i, s);
                     if (s.elapsed == 0) {
-                        float4 a = A.st.va[i]; float2 b = A.st.vb[i];
-                        vel[0] = a.x; vel[1] = a.y; vel[2] = a.z; vel[3] = a.w; vel[4] = b.x; vel[5] = b.y;
+                        load_vel(A.st, i, vel);
                     } else {
 #pragma unroll
                         for (int k = 0; k < 6; k++) vel[k] = s.elapsed <= 25 ? s.C[8 + k] : 0.0f;
                     }
                 }
-                A.st.va[i] = make_float4(vel[0], vel[1], vel[2], vel[3]);
-                A.st.vb[i] = make_float2(vel[4], vel[5]);
+                store_vel(A.st, i, vel);
 #pragma unroll
                 for (int k = 0; k < 6; k++) row[24 + k] = vel[k];
             }
@@ -543,8 +564,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_observe_kernel(const __grid
     load_hot<TASK>(A.st, i, s);
     float stale[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     if (TT::DYN) {
-        float4 a = A.st.va[i]; float2 b = A.st.vb[i];
-        stale[0] = a.x; stale[1] = a.y; stale[2] = a.z; stale[3] = a.w; stale[4] = b.x; stale[5] = b.y;
+        load_vel(A.st, i, stale);
     }
     float row[TT::OBS];
     env_observe<TASK, GEOM_CAPSULE>(c_model, s, stale, row);
