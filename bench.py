@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--task", default="UR5DynReach-v1", choices=sorted(OBS_DIM))
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--geometry", default="capsule", choices=["capsule", "hull"])
-    ap.add_argument("--chains", type=int, default=4, help="independent env sub-ranges per GPU in the captured graph (1..8)")
+    ap.add_argument("--chains", type=int, default=2, help="independent env sub-ranges per GPU in the captured graph (1..8)")
     ap.add_argument("--graph-steps", type=int, default=32, help="env steps captured per CUDA graph replay (multiple of 8)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall-clock budget of the cpu_baseline sample")
