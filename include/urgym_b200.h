@@ -50,7 +50,10 @@ enum { URGYM_F_Q = 0,            /* float [N,6]  joint angles                   
        URGYM_F_ELAPSED = 5,      /* int32 [N]    TimeLimit counter == ReachDyn.step_num        */
        URGYM_F_EP_RETURN = 6,    /* float [N]    running episode return                        */
        URGYM_F_VELOCITY = 7,     /* float [N,6]  ReachDyn.velocity carried over the last reset (reach.py:664-683 never clears it) */
-       URGYM_F_COUNT = 8 };
+       URGYM_F_HOT = 8,          /* float [N,24] the step kernel's copy of the episode constants + episode cache (derived
+                                    from GOAL / OBSTACLE / OBSTACLE_END whenever those are set; raw words, for
+                                    checkpoints: restoring it after the other fields makes a restore bit-exact) */
+       URGYM_F_COUNT = 9 };
 
 #define URGYM_OK 0
 #define URGYM_EINVAL (-1)     /* bad argument                         */

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("URGYM_B200_LIB") or os.path.join(_HERE, "liburgym_b20
 TASK_IDS = {"UR5OriReach-v1": 0, "UR5ObsReach-v1": 1, "UR5StaReach-v1": 2, "UR5DynReach-v1": 3}
 GEOM_HULL, GEOM_CAPSULE = 0, 1
 GEOMS = {"hull": GEOM_HULL, "capsule": GEOM_CAPSULE}
-(F_Q, F_GOAL, F_OBSTACLE, F_OBSTACLE_END, F_LINK_DIST, F_ELAPSED, F_EP_RETURN, F_VELOCITY) = range(8)
+(F_Q, F_GOAL, F_OBSTACLE, F_OBSTACLE_END, F_LINK_DIST, F_ELAPSED, F_EP_RETURN, F_VELOCITY, F_HOT) = range(9)
 STATS_COUNT = 8
 STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions", "truncations", "env_steps",
               "reset_iterations")

@@ -63,6 +63,10 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_field_kernel(const FieldArg
         for (int k = 0; k < 2; k++) mv(b + k, x + i * 6 + 4 + k);
         break;
     }
+    case URGYM_F_HOT:
+        for (int k = 0; k < 24; k++)
+            mv(reinterpret_cast<float *>(&A.st.h8[k / 8][2 * i + (k % 8) / 4]) + (k % 4), x + i * 24 + k);
+        break;
     default: break;
     }
 }
@@ -133,8 +137,12 @@ static const aux_launcher_t k_autoreset[2][4] = {
 static const aux_launcher_t k_refresh[2][4] = {
     {urgym_inst_refresh_0_0, urgym_inst_refresh_1_0, urgym_inst_refresh_2_0, urgym_inst_refresh_3_0},
     {urgym_inst_refresh_0_1, urgym_inst_refresh_1_1, urgym_inst_refresh_2_1, urgym_inst_refresh_3_1}};
-static const aux_launcher_t k_observe[4] = {launch_observe<0>, launch_observe<1>, launch_observe<2>, launch_observe<3>};
-static const aux_launcher_t k_derive[4] = {launch_derive<0>, launch_derive<1>, launch_derive<2>, launch_derive<3>};
+static const aux_launcher_t k_observe[2][4] = {
+    {urgym_inst_observe_0_0, urgym_inst_observe_1_0, urgym_inst_observe_2_0, urgym_inst_observe_3_0},
+    {urgym_inst_observe_0_1, urgym_inst_observe_1_1, urgym_inst_observe_2_1, urgym_inst_observe_3_1}};
+static const aux_launcher_t k_derive[2][4] = {
+    {urgym_inst_derive_0_0, urgym_inst_derive_1_0, urgym_inst_derive_2_0, urgym_inst_derive_3_0},
+    {urgym_inst_derive_0_1, urgym_inst_derive_1_1, urgym_inst_derive_2_1, urgym_inst_derive_3_1}};
 
 static const aux_launcher_t k_prepare[2][4] = {
     {urgym_inst_prepare_0_0, urgym_inst_prepare_1_0, urgym_inst_prepare_2_0, urgym_inst_prepare_3_0},
@@ -381,7 +389,7 @@ extern "C" int urgym_observe(urgym_env_t *h, float *obs, float *achieved, float 
     AuxArgs A;
     memset(&A, 0, sizeof(A));
     A.st = h->st; A.n = h->n; A.offset = h->offset; A.obs = obs; A.ach = achieved; A.des = desired;
-    CK(k_observe[h->task](h->model, A, (cudaStream_t)stream));
+    CK(k_observe[h->geom][h->task](h->model, A, (cudaStream_t)stream));
     h->launches++;
     return URGYM_OK;
 }
@@ -419,7 +427,7 @@ static int field_io(urgym_env *h, int field, void *ext, int to_state, void *stre
         AuxArgs D;
         memset(&D, 0, sizeof(D));
         D.st = h->st; D.n = h->n;
-        CK(k_derive[h->task](h->model, D, (cudaStream_t)stream));
+        CK(k_derive[h->geom][h->task](h->model, D, (cudaStream_t)stream));
         h->launches++;
     }
     return URGYM_OK;

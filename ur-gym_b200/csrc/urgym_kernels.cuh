@@ -663,6 +663,8 @@ typedef cudaError_t (*aux_launcher_t)(const ModelConst &, const AuxArgs &, cudaS
     cudaError_t urgym_inst_reset_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);   \
     cudaError_t urgym_inst_autoreset_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);   \
     cudaError_t urgym_inst_refresh_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);      \
+    cudaError_t urgym_inst_observe_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);      \
+    cudaError_t urgym_inst_derive_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);       \
     cudaError_t urgym_inst_prepare_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);
 URGYM_DECLARE_INST(0, 0) URGYM_DECLARE_INST(1, 0) URGYM_DECLARE_INST(2, 0) URGYM_DECLARE_INST(3, 0)
 URGYM_DECLARE_INST(0, 1) URGYM_DECLARE_INST(1, 1) URGYM_DECLARE_INST(2, 1) URGYM_DECLARE_INST(3, 1)

@@ -162,7 +162,8 @@ class UR5VecEnv:
     _FIELDS = {"q": (nat.F_Q, 6, torch.float32), "goal": (nat.F_GOAL, None, torch.float32),
                "obstacle": (nat.F_OBSTACLE, 6, torch.float32), "obstacle_end": (nat.F_OBSTACLE_END, 6, torch.float32),
                "link_dist": (nat.F_LINK_DIST, 5, torch.float32), "elapsed": (nat.F_ELAPSED, 0, torch.int32),
-               "ep_return": (nat.F_EP_RETURN, 0, torch.float32), "velocity": (nat.F_VELOCITY, 6, torch.float32)}
+               "ep_return": (nat.F_EP_RETURN, 0, torch.float32), "velocity": (nat.F_VELOCITY, 6, torch.float32),
+               "hot": (nat.F_HOT, 24, torch.float32)}
 
     def _field(self, name):
         fid, k, dt = self._FIELDS[name]
@@ -201,7 +202,9 @@ class UR5VecEnv:
             names += ["obstacle_end", "velocity"]
         ev = ctypes.c_uint32()
         nat.check(self.h, self.L.urgym_get_event(self.h, ctypes.byref(ev)))
-        d = {k: self.get_state(k) for k in names}
+        # "hot" (the step kernel's episode cache) last: it is re-derived whenever a goal / obstacle field is set, and the
+        # raw words restored afterwards make the restore bit-exact
+        d = {k: self.get_state(k) for k in names + ["hot"]}
         d["event"] = int(ev.value)
         return d
 
