@@ -55,7 +55,7 @@ URGYM_HD void sincos_fast(float x, float *s, float *c) {
 // atan2 with 3e-7 absolute accuracy in ~25 instructions (libdevice's is ~55 and is called 8 times per env step):
 // reduce to t = min(|x|,|y|)/max(|x|,|y|) in [0,1], minimax odd polynomial for atan(t), undo the reductions.
 // The host instantiation uses libm.
-static URGYM_OOL float atan2_fast(float y, float x) {
+URGYM_HD float atan2_inl(float y, float x) {
 #ifdef __CUDA_ARCH__
     float ax = fabsf(x), ay = fabsf(y);
     float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
@@ -79,6 +79,12 @@ static URGYM_OOL float atan2_fast(float y, float x) {
 #else
     return atan2f(y, x);
 #endif
+}
+static URGYM_OOL float atan2_fast(float y, float x) { return atan2_inl(y, x); }
+// three atan2 in one out-of-line call (roll, pitch, yaw): the Euler extractions need three at a time, their polynomials
+// (serial chains of nine FMAs each) interleave, and two call / return pairs go away (-1.4 % step-kernel time)
+static URGYM_OOL float3 atan2_fast_x3(float y0, float x0, float y1, float x1, float y2, float x2) {
+    return make_float3(atan2_inl(y0, x0), atan2_inl(y1, x1), atan2_inl(y2, x2));
 }
 URGYM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
@@ -241,9 +247,7 @@ URGYM_HD float3 euler_from_quat(Quat q) {
         // pitch = asin(sarg), evaluated as atan2(sin, cos) with cos(pitch) = |(R21, R22)|: same angle, but not
         // ill-conditioned in FP32 when |pitch| approaches 90 degrees
         float r21 = 2.0f * (q.y * q.z + q.w * q.x), r22 = squ - sqx - sqy + sqz;
-        e.y = atan2_fast(sarg, sqrtf(r21 * r21 + r22 * r22));
-        e.x = atan2_fast(r21, r22);
-        e.z = atan2_fast(2.0f * (q.x * q.y + q.w * q.z), squ + sqx - sqy - sqz);
+        e = atan2_fast_x3(r21, r22, sarg, sqrtf(r21 * r21 + r22 * r22), 2.0f * (q.x * q.y + q.w * q.z), squ + sqx - sqy - sqz);
     }
     return e;
 }
@@ -376,6 +380,18 @@ URGYM_HD void fkp_advance(const ModelConst &M, PoseP &T, int j, float qj) {
     T.z01 = f2(fmaf(az.x, c, az.y * s), fmaf(az.y, c, -az.x * s));
     T.z2 = az2;
 }
+// joint 0 from the identity pose: R = F Rz(q), p = x  (a third of the general step's instructions)
+URGYM_HD void fkp_first(const ModelConst &M, PoseP &T, float q0) {
+    const float (*F)[4] = M.joint_rot_p[0];
+    float s, c;
+    sincos_fast(q0, &s, &c);
+    T.c0 = fma2(f2(F[0][0], F[1][0]), bc2(c), mul2(f2(F[0][1], F[1][1]), bc2(s)));
+    T.c1 = fma2(f2(F[0][1], F[1][1]), bc2(c), mul2(f2(F[0][0], F[1][0]), bc2(-s)));
+    T.c2 = f2(F[0][2], F[1][2]);
+    T.z01 = f2(fmaf(F[2][0], c, F[2][1] * s), fmaf(F[2][1], c, -F[2][0] * s));
+    T.z2 = F[2][2];
+    T.pxy = f2(M.joint_xyz[0][0], M.joint_xyz[0][1]); T.pz = M.joint_xyz[0][2];
+}
 // world capsule segment of link l: a = p + R cap_p0, b = p + R cap_p1; returns (a.x, a.y), (b.x, b.y), (a.z, b.z)
 URGYM_HD void capsule_world(const ModelConst &M, const PoseP &T, int l, float2 &axy, float2 &bxy, float2 &abz) {
     const float (*P)[2] = M.cap_pp[l];
@@ -388,7 +404,7 @@ URGYM_HD void capsule_world(const ModelConst &M, const PoseP &T, int l, float2 &
 URGYM_HD float3 euler_from_posep(const PoseP &T) {
     const float sarg = -T.z01.x;
     if (fabsf(sarg) < 0.99f)
-        return f3(atan2_fast(T.z01.y, T.z2), atan2_fast(sarg, sqrtf(T.z01.y * T.z01.y + T.z2 * T.z2)), atan2_fast(T.c0.y, T.c0.x));
+        return atan2_fast_x3(T.z01.y, T.z2, sarg, sqrtf(T.z01.y * T.z01.y + T.z2 * T.z2), T.c0.y, T.c0.x);
     const float R[9] = {T.c0.x, T.c1.x, T.c2.x, T.c0.y, T.c1.y, T.c2.y, T.z01.x, T.z01.y, T.z2};
     return euler_via_quat_ool(R);
 }

@@ -372,7 +372,8 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
     posep_identity(T);
 #pragma unroll
     for (int l = 1; l < 7; l++) {
-        fkp_advance(M, T, l - 1, q[l - 1]);
+        if (l == 1) fkp_first(M, T, q[0]);          // from the identity pose: a third of the general step
+        else fkp_advance(M, T, l - 1, q[l - 1]);
         if (collide) {
             float2 axy, bxy, abz;
             capsule_world(M, T, l, axy, bxy, abz);
