@@ -387,7 +387,7 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
     bool hit = false;
     unsigned slow = 0u;
     // links 2..6 vs obstacle (distances kept: they are get_link_distances' values), table and track
-#pragma unroll 1
+#pragma unroll 2     // two links per trip: their dependent chains interleave (-0.8 %); fully unrolled it spills (-21 %)
     for (int l = 2; l < 7; l++) {
         const float *c = cap + (l - 1) * 6 * cs;
         const float3 a = f3(c[0], c[cs], c[2 * cs]), b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
