@@ -200,7 +200,11 @@ def run_ours(args, rank, world, local_rank):
     graph.replay()
     env.stats(reset=True)
     steps = max(args.steps, 1)
-    n_replays, rem = divmod(steps, gs)                # exactly `steps` env steps: whole replays + eager remainder
+    n_replays, rem = divmod(steps, gs)                # exactly `steps` env steps: whole replays + a shorter graph
+    graph_rem = env.capture_steps([ring[k % 8] for k in range(rem)], chains=chains) if rem else None
+    if graph_rem is not None:
+        graph_rem.replay()
+        env.stats(reset=True)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -215,8 +219,8 @@ def run_ours(args, rank, world, local_rank):
     e0.record()
     for k in range(n_replays):
         graph.replay()
-    for k in range(rem):
-        env.step(ring[k % 8])
+    if graph_rem is not None:
+        graph_rem.replay()
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
@@ -231,8 +235,6 @@ def run_ours(args, rank, world, local_rank):
         clock_note = "timed region shorter than the sampler period: sampled during an untimed 0.25 s repeat of the same loop"
     sampler.stop_flag = True
     launches = 2 * steps * chains                     # step kernel + auto-reset kernel per env step and chain
-    if rem:
-        launches -= 2 * rem * (chains - 1)            # the eager remainder steps are whole-batch launches
     barrier()
     env.stats(reset=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
