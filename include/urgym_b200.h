@@ -39,6 +39,13 @@ enum { URGYM_TASK_ORI = 0,   /* UR5OriReach-v1  ReachOri  reach.py:141-236  obs 
 enum { URGYM_GEOM_HULL = 0,     /* the reference's convex-hull links + cylinder/box scene, GJK distances */
        URGYM_GEOM_CAPSULE = 1 };/* bounding capsules for links, capsule obstacle: closed-form distances (approximate) */
 
+/* what `link_dist` (observation columns, reward term) measures: PyBullet.get_link_distances, pyb_setup.py:439-456 */
+enum { URGYM_LD_OBSTACLE = 0,   /* links 2..6 vs the obstacle: the code the reference ships (default)                  */
+       URGYM_LD_WORKBENCH = 1 };/* per link min(obstacle, table, track): what the method's docstring describes ("distance
+                                   between workbench, obstacle and UR5"); the definition under which the policies shipped
+                                   in Trained_Models/Trained_{Obs,Sta} (2023-09, older than the shipped code) reproduce
+                                   their published success rates -- DESIGN.md section 2 */
+
 /* state fields for urgym_get_state / urgym_set_state: the injection hooks of the reference
  * (robot.set_joint_angles core.py:161-167; task.set_goal reach.py:202-204; task.set_goal_and_obstacle
  * reach.py:328-335,483-503,702-713) and a checkpoint of the whole simulator. */
@@ -145,6 +152,9 @@ int urgym_reset_host(urgym_env_t *h, const uint8_t *mask, float *obs, float *ach
 /* auto-reset on (default, DummyVecEnv semantics) or off (a bare RobotTaskEnv: finished envs keep their state and
  * keep stepping until the caller resets them, core.py:303-317). */
 int urgym_set_autoreset(urgym_env_t *h, int enabled);
+/* URGYM_LD_*; takes effect with the next launch: call urgym_refresh afterwards so that link_dist = last_dist are
+ * re-measured in the new mode.  URGYM_EUNSUPPORTED for UR5OriReach (no obstacle, no link_dist). */
+int urgym_set_link_dist_mode(urgym_env_t *h, int mode);
 /* the reset-event counter (position of the reset stream); together with the URGYM_F_* fields it checkpoints a handle */
 int urgym_get_event(const urgym_env_t *h, uint32_t *event);
 /* re-key the reset stream: RobotTaskEnv.reset(seed=...) re-creates task.np_random (core.py:267) */

@@ -36,6 +36,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libur_oracle.so")
 
 GEOM_HULL, GEOM_CAPSULE = 0, 1
+# what PyBullet.get_link_distances measures (pyb_setup.py:439-456).  LD_OBSTACLE: the code as the reference ships it --
+# links 2..6 against the obstacle only.  LD_WORKBENCH: what the method's own docstring describes ("Check the distance
+# between workbench, obstacle and UR5 ... Array of robot links to any obstacle"): per link the smallest of the
+# distances to the obstacle, the table and the track.  The shipped UR5ObsReach / UR5StaReach policies (September 2023,
+# nine months older than the shipped code and the UR5DynReach policy) only reproduce their published success rates
+# with the second definition; see DESIGN.md section 2.
+LD_OBSTACLE, LD_WORKBENCH = 0, 1
 
 
 def build_oracle(force: bool = False) -> str:
@@ -210,8 +217,9 @@ class OracleSim:
       joint_limits=False   URDF limits are not enforced by the teleport path
     """
 
-    def __init__(self, geom: int = GEOM_HULL, n_substeps: int = 20):
+    def __init__(self, geom: int = GEOM_HULL, n_substeps: int = 20, link_dist_mode: int = LD_OBSTACLE):
         self.geom = geom
+        self.link_dist_mode = link_dist_mode
         self.n_substeps = n_substeps                  # pyb_setup.py:25
         self.timestep = 1.0 / 500                     # pyb_setup.py:40
         self._bodies: Dict[str, dict] = {}            # insertion order == _bodies_idx order
@@ -340,7 +348,11 @@ class OracleSim:
     def get_link_distances(self) -> np.ndarray:                    # pyb_setup.py:439-456
         out = _d(5)
         self.last_deep_mask = lib().orc_link_distances(ctypes.byref(self._scene()), out)
-        return np.array(out[:])
+        d = np.array(out[:])
+        if self.link_dist_mode == LD_WORKBENCH:         # links 2..6 vs table (pairs 5..9) and track (pairs 10..14)
+            a = self.all_pair_distances()
+            d = np.minimum(d, np.minimum(a[5:10], a[10:15]))
+        return d
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -641,10 +653,10 @@ class OracleEnv:
     max_episode_steps = 100
 
     def __init__(self, env_id: str, geom: int = GEOM_HULL, stream: Optional[UniformStream] = None,
-                 env_index: int = 0, first_event: Optional[int] = None):
+                 env_index: int = 0, first_event: Optional[int] = None, link_dist_mode: int = LD_OBSTACLE):
         assert env_id in TASKS, env_id
         self.spec_id = env_id
-        self.sim = OracleSim(geom=geom)
+        self.sim = OracleSim(geom=geom, link_dist_mode=link_dist_mode)
         self.robot = UR5Ori(self.sim)
         self.task = ReachTask(self.sim, self.robot, env_id, stream or NumpyStream(0), env_index)
         self._elapsed_steps = 0

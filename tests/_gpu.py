@@ -6,9 +6,10 @@ import urgym_b200 as ug
 
 
 class GpuSim:
-    def __init__(self, env_id, geom, n, seed=0, offset=0, autoreset=True, device=0):
+    def __init__(self, env_id, geom, n, seed=0, offset=0, autoreset=True, device=0, link_dist_mode=0):
         self.vec = ug.UR5VecEnv(env_id, n, device=device, seed=seed, env_index_offset=offset,
-                                geometry="capsule" if geom == 1 else "hull", auto_reset=autoreset)
+                                geometry="capsule" if geom == 1 else "hull", auto_reset=autoreset,
+                                link_dist="workbench" if link_dist_mode else "obstacle")
         self.n = n
 
     def reset(self):

@@ -29,8 +29,9 @@ def _p(a):
 
 
 class HostCheckSim:
-    def __init__(self, env_id, geom, n, seed=0, offset=0, autoreset=True):
+    def __init__(self, env_id, geom, n, seed=0, offset=0, autoreset=True, link_dist_mode=0):
         self.task, self.geom, self.n, self.seed, self.offset = TASK_ID[env_id], geom, n, seed, offset
+        self.link_dist_mode = link_dist_mode
         self.D, self.G = OBS_DIM[self.task], GOAL_DIM[self.task]
         self.q = np.zeros((n, 6), np.float32); self.elapsed = np.zeros(n, np.int32); self.ep_ret = np.zeros(n, np.float32)
         self.ld = np.zeros((n, 5), np.float32); self.E = np.zeros((n, 18), np.float32)
@@ -38,6 +39,7 @@ class HostCheckSim:
         self.event = 0
         self.autoreset = autoreset
         self.L = lib(geom)
+        self.L.hc_set_ld_mode(link_dist_mode)       # library-global: one HostCheckSim per mode at a time
 
     def _state_ptrs(self, idx=None):
         return [_p(self.q), _p(self.elapsed), _p(self.ep_ret), _p(self.ld), _p(self.E)]

@@ -65,9 +65,10 @@ def obs_close(env_id, got, want, ld_tol=None):
 
 
 class OracleBatch:
-    def __init__(self, env_id, geom, n, seed, offset=0, first_event=1):
+    def __init__(self, env_id, geom, n, seed, offset=0, first_event=1, link_dist_mode=0):
         self.env_id = env_id
-        self.envs = [oe.make(env_id, geom=geom, stream=oe.PhiloxStream(seed), env_index=offset + i, first_event=first_event)
+        self.envs = [oe.make(env_id, geom=geom, stream=oe.PhiloxStream(seed), env_index=offset + i, first_event=first_event,
+                             link_dist_mode=link_dist_mode)
                      for i in range(n)]
 
     def first_obs(self):
@@ -87,9 +88,9 @@ class OracleBatch:
 
 
 def run_parity(sim, env_id, geom, n, steps, seed, offset=0, action_scale=1.2, rng_seed=0, check_terminal=True,
-               ld_tol=None, rew_atol=0.0):
+               ld_tol=None, rew_atol=0.0, link_dist_mode=0):
     """sim: .reset() -> obs [n,D]; .step(a) -> dict(obs, reward, terminated, truncated, is_success, terminal_obs)."""
-    orc = OracleBatch(env_id, geom, n, seed, offset, first_event=1)
+    orc = OracleBatch(env_id, geom, n, seed, offset, first_event=1, link_dist_mode=link_dist_mode)
     obs = sim.reset()
     event = 1
     alive = np.ones(n, bool)

@@ -1,37 +1,64 @@
 """Closed-loop statistical check with the policies the reference ships.
 
-The reference publishes, for each task, the success rate and mean episode reward of its trained SAC policy over ~5 k
-scenarios run in real PyBullet (model_test.py:26-61 with utils/generate.py:23-102; numbers in
+The reference publishes, for each task, the success rate and per-episode (reward, success, steps) lines of its trained
+SAC policy over ~5 k scenarios run in real PyBullet (model_test.py:26-61 with utils/generate.py:23-102; numbers in
 Trained_Models/*/best.txt).  Those scenarios were random and not saved, so this is a *statistical* pin -- but it is
-the only number in the reference that real PyBullet produced, and a policy trained on PyBullet observations only
-succeeds here if frames, Euler conventions, link indexing, observation layout and obstacle geometry match.
+the only output of real PyBullet the reference contains, and a policy trained on PyBullet observations only
+succeeds here if frames, Euler conventions, link indexing, observation layout and scene geometry match.
 
 Protocol (model_test.py:26-61): reset; inject the scenario; deterministic policy for at most 100 steps; an episode
 ends at the first terminated step (or step 99); success = info["is_success"] there; reward summed up to there.
 Scenarios (utils/generate.py): Ori -- goal positions on a 0.05 m grid x 5 random goal orientations;
 Obs / Sta -- 5 000 natural resets; Dyn -- goal on the grid, obstacle start / end re-sampled until the target-to-end
-distance is >= 0.1 m and start-end >= 0.3 m (reach.py:685-700)."""
+distance is >= 0.1 m and start-end >= 0.3 m (reach.py:685-700).
+
+LINK-DISTANCE MODE.  UR5ObsReach and UR5StaReach are run with link_dist="workbench" (per link the smallest distance to
+obstacle, table and track).  Round 2's diagnosis (profiles/closed_loop_r02.json): the two policies
+are quasi-linear in their five link_dist inputs; fed the distances the shipped get_link_distances computes (obstacle
+only, pyb_setup.py:439-456) they dive wrist_1 into the table (Obs: 30 % collisions, all `wrist_1 - table`) or stall with
+a constant action bias 5-8 cm beside the goal (Sta: 28 % time-outs); fed what the method's docstring describes ("distance
+between workbench, obstacle and UR5 ... robot links to any obstacle") they reproduce the published success rate, time-out
+share, collision share and step histogram (and, for Obs, the published reward sum, which contains the link_dist term).
+Their zips carry start_time 2023-09-20/21; the UR5DynReach zip, 2024-06-07, works with the shipped definition."""
 import json
 import os
 import sys
 
 import numpy as np
-import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 SHORT = {"UR5OriReach-v1": "Ori", "UR5ObsReach-v1": "Obs", "UR5StaReach-v1": "Sta", "UR5DynReach-v1": "Dyn"}
+LD_COLS = {"UR5ObsReach-v1": (21, 26), "UR5StaReach-v1": (24, 29), "UR5DynReach-v1": (30, 35)}
+STEP_BINS = [0, 3, 5, 7, 9, 12, 16, 25, 50, 100]
+# the link-distance definition each shipped policy is evaluated with (see the module docstring)
+POLICY_LINK_DIST = {"UR5OriReach-v1": "obstacle", "UR5ObsReach-v1": "workbench", "UR5StaReach-v1": "workbench",
+                    "UR5DynReach-v1": "obstacle"}
+
+
+def load_policy_numpy(env_id):
+    w = np.load(os.path.join(ROOT, "tests", "golden", f"policy_{SHORT[env_id]}.npz"))
+    t = {k: w[k].astype(np.float32) for k in w.files if not k.startswith("published")}
+    pub = {k: (w[k].tolist() if w[k].ndim else float(w[k])) for k in w.files if k.startswith("published")}
+
+    def act(ag, dg, obs):
+        # SB3 CombinedExtractor: Dict space keys in sorted order -> achieved_goal, desired_goal, observation
+        x = np.concatenate([ag, dg, obs], axis=1)
+        h = np.maximum(x @ t["latent_pi_0_weight"].T + t["latent_pi_0_bias"], 0)
+        h = np.maximum(h @ t["latent_pi_2_weight"].T + t["latent_pi_2_bias"], 0)
+        return np.tanh(h @ t["mu_weight"].T + t["mu_bias"]).astype(np.float32)
+    return act, pub
 
 
 def load_policy(env_id, device):
+    import torch
     w = np.load(os.path.join(ROOT, "tests", "golden", f"policy_{SHORT[env_id]}.npz"))
     t = {k: torch.as_tensor(w[k], device=device) for k in w.files if not k.startswith("published")}
-    pub = {k: float(w[k]) for k in w.files if k.startswith("published")}
+    pub = {k: (w[k].tolist() if w[k].ndim else float(w[k])) for k in w.files if k.startswith("published")}
 
     def act(obs):
-        # SB3 CombinedExtractor: Dict space keys in sorted order -> achieved_goal, desired_goal, observation
         x = torch.cat([obs["achieved_goal"], obs["desired_goal"], obs["observation"]], dim=1)
         h = torch.relu(x @ t["latent_pi_0_weight"].T + t["latent_pi_0_bias"])
         h = torch.relu(h @ t["latent_pi_2_weight"].T + t["latent_pi_2_bias"])
@@ -68,10 +95,31 @@ def dyn_scenarios(goal_pos, seed=0):
     return out
 
 
-def run(env_id, geometry="capsule", seed=0, device=0, max_envs=None):
+def taxonomy(success, collided, steps, ret, pub, extra=None):
+    """the figures the published per-episode lines allow to compare (tests/golden/make_policy_fixtures.py)"""
+    success, collided = np.asarray(success, bool), np.asarray(collided, bool)
+    steps, ret = np.asarray(steps), np.asarray(ret, np.float64)
+    res = {"episodes": int(len(success)), "success_rate_pct": 100.0 * float(success.mean()),
+           "mean_reward": float(ret.mean()), "collision_rate_pct": 100.0 * float(collided.mean()),
+           "timeout_pct": 100.0 * float((~success & ~collided).mean()), "mean_steps": float(steps.mean()),
+           "success_mean_steps": float(steps[success].mean()) if success.any() else None,
+           "success_mean_reward": float(ret[success].mean()) if success.any() else None,
+           "success_step_hist": np.histogram(steps[success], bins=STEP_BINS)[0].tolist(),
+           "collision_mean_steps": float(steps[collided].mean()) if collided.any() else None,
+           "published": pub}
+    if extra:
+        res.update(extra)
+    return res
+
+
+def run(env_id, geometry="capsule", seed=0, device=0, max_envs=None, link_dist=None, ld_ablation=None):
+    """GPU run through the public batched API.  ld_ablation: None, "zero" (link_dist inputs of the POLICY set to 0) or
+    "clip0.2" (min(link_dist, 0.2)): the policy-input ablations of the round-2 diagnosis; the simulator is untouched."""
+    import torch
     import urgym_b200 as ug
     dev = torch.device("cuda", device)
     act, pub = load_policy(env_id, dev)
+    link_dist = link_dist or POLICY_LINK_DIST[env_id]
     if env_id in ("UR5OriReach-v1", "UR5DynReach-v1"):
         low = [0.3, -0.5, 0.0] if env_id == "UR5OriReach-v1" else [0.4, -0.5, 0.0]
         pos = grid_positions(np.array(low), np.array([0.75, 0.5, 0.2]))
@@ -80,7 +128,7 @@ def run(env_id, geometry="capsule", seed=0, device=0, max_envs=None):
         n = 5000
     if max_envs:
         n = min(n, max_envs)
-    env = ug.UR5VecEnv(env_id, n, device=device, seed=seed, geometry=geometry, auto_reset=False)
+    env = ug.UR5VecEnv(env_id, n, device=device, seed=seed, geometry=geometry, auto_reset=False, link_dist=link_dist)
     env.reset()
     if env_id == "UR5OriReach-v1":
         goal = env.get_state("goal")
@@ -98,7 +146,13 @@ def run(env_id, geometry="capsule", seed=0, device=0, max_envs=None):
     ret = torch.zeros(n, dtype=torch.float64, device=dev)
     steps = torch.zeros(n, dtype=torch.int32, device=dev)
     for t in range(100):
-        obs, rew, term, trunc, info = env.step(act(obs))
+        pol_obs = obs
+        if ld_ablation and env_id in LD_COLS:
+            a, b = LD_COLS[env_id]
+            o = obs["observation"].clone()
+            o[:, a:b] = 0.0 if ld_ablation == "zero" else torch.clamp(o[:, a:b], max=0.2)
+            pol_obs = {"observation": o, "achieved_goal": obs["achieved_goal"], "desired_goal": obs["desired_goal"]}
+        obs, rew, term, trunc, info = env.step(act(pol_obs))
         live = ~finished
         ret += torch.where(live, rew.double(), torch.zeros_like(ret))
         ends = live & (term.bool() | (t == 99))
@@ -106,12 +160,42 @@ def run(env_id, geometry="capsule", seed=0, device=0, max_envs=None):
         collided |= ends & term.bool() & ~info["is_success"].bool()
         steps = torch.where(ends, torch.full_like(steps, t), steps)
         finished |= ends
-    res = {"env_id": env_id, "geometry": geometry, "episodes": n,
-           "success_rate_pct": 100.0 * float(success.double().mean()), "mean_reward": float(ret.mean()),
-           "collision_rate_pct": 100.0 * float(collided.double().mean()), "mean_steps": float(steps.double().mean()),
-           "published": pub}
+    res = taxonomy(success.cpu().numpy(), collided.cpu().numpy(), steps.cpu().numpy(), ret.cpu().numpy(), pub,
+                   {"env_id": env_id, "geometry": geometry, "link_dist": link_dist, "policy_ld_ablation": ld_ablation})
     env.close()
     return res
+
+
+def run_host(env_id, geom=1, n=500, seed=0, link_dist_mode=0, ld_ablation=None):
+    """The same protocol on tests/hostcheck (the product's per-env code compiled for the host): the CPU tier's
+    closed-loop check, natural-reset scenarios for every task."""
+    from tests._hostcheck import HostCheckSim, GOAL_DIM, TASK_ID
+    act, pub = load_policy_numpy(env_id)
+    sim = HostCheckSim(env_id, geom, n, seed=seed, autoreset=False, link_dist_mode=link_dist_mode)
+    obs = sim.reset()
+    G = GOAL_DIM[TASK_ID[env_id]]
+    finished = np.zeros(n, bool); success = np.zeros(n, bool); collided = np.zeros(n, bool)
+    steps = np.zeros(n, int); ret = np.zeros(n)
+    for t in range(100):
+        o = obs.copy()
+        if ld_ablation and env_id in LD_COLS:
+            a, b = LD_COLS[env_id]
+            o[:, a:b] = 0.0 if ld_ablation == "zero" else np.minimum(o[:, a:b], 0.2)
+        out = sim.step(act(o[:, :G], o[:, 12:12 + G], o))
+        obs = out["obs"]
+        live = ~finished
+        ret += np.where(live, out["reward"], 0)
+        ends = live & (out["terminated"] | (t == 99))
+        success |= ends & out["is_success"]
+        collided |= ends & out["collision"]
+        steps[ends] = t
+        finished |= ends
+        if finished.all():
+            break
+    return taxonomy(success, collided, steps, ret, pub,
+                    {"env_id": env_id, "geometry": "capsule" if geom == 1 else "hull",
+                     "link_dist": "workbench" if link_dist_mode else "obstacle", "policy_ld_ablation": ld_ablation,
+                     "scenarios": "natural resets (host instantiation)"})
 
 
 if __name__ == "__main__":
@@ -120,7 +204,16 @@ if __name__ == "__main__":
         for env_id in SHORT:
             r = run(env_id, geometry)
             out.append(r)
-            print(json.dumps(r), flush=True)
+            print(json.dumps({k: v for k, v in r.items() if k != "published"}), flush=True)
+    # the diagnosis: the shipped definition and the two policy-input ablations, hull geometry
+    for env_id in ("UR5ObsReach-v1", "UR5StaReach-v1", "UR5DynReach-v1"):
+        for kw in (dict(link_dist="obstacle"), dict(link_dist="obstacle", ld_ablation="zero"),
+                   dict(link_dist="obstacle", ld_ablation="clip0.2"), dict(link_dist="workbench")):
+            if env_id != "UR5DynReach-v1" and kw == dict(link_dist="workbench"):
+                continue        # already in the first block
+            r = run(env_id, "hull", **kw)
+            out.append(r)
+            print(json.dumps({k: v for k, v in r.items() if k != "published"}), flush=True)
     path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "closed_loop.json")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     json.dump(out, open(path, "w"), indent=1)

@@ -10,6 +10,7 @@ features = concat(achieved_goal, desired_goal, observation) -> Linear 256 -> ReL
 Trained_Models/Trained_{Ori,Obs,Sta}/best.txt:1-2 and Trained_Models/Trained_Dyn/best_modeltest_result.txt:1-2
 (success rate and mean episode reward over the model_test.py scenarios)."""
 import io
+import json
 import os
 import re
 import sys
@@ -20,6 +21,7 @@ import torch
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
+STEP_BINS = [0, 3, 5, 7, 9, 12, 16, 25, 50, 100]
 RESULT = {"Ori": "best.txt", "Obs": "best.txt", "Sta": "best.txt", "Dyn": "best_modeltest_result.txt"}
 
 for t in ("Ori", "Obs", "Sta", "Dyn"):
@@ -34,5 +36,17 @@ for t in ("Ori", "Obs", "Sta", "Dyn"):
     eps = np.array([[float(x) for x in l.replace(" ", "").split(",")] for l in lines[2:] if l.strip()])
     out["published_episodes"] = np.int64(len(eps))
     out["published_mean_steps"] = np.float64(eps[:, 2].mean())
+    # failure taxonomy of the published per-episode lines (reward, success, last step index): model_test.py:40-60
+    rew, ok, st = eps[:, 0], eps[:, 1] == 1, eps[:, 2]
+    out["published_timeout_pct"] = np.float64(100.0 * ((st == 99) & ~ok).mean())
+    out["published_collision_pct"] = np.float64(100.0 * ((st < 99) & ~ok).mean())
+    out["published_success_mean_steps"] = np.float64(st[ok].mean())
+    out["published_success_mean_reward"] = np.float64(rew[ok].mean())
+    out["published_success_step_hist"] = np.histogram(st[ok], bins=STEP_BINS)[0].astype(np.int64)
+    out["published_collision_mean_steps"] = np.float64(st[(st < 99) & ~ok].mean())
+    # when the policy was trained (SB3 `start_time`, ns since the epoch) and with which library versions
+    meta = json.loads(z.read("data"))
+    out["published_train_start_ns"] = np.int64(meta["start_time"])
+    out["published_num_timesteps"] = np.int64(meta["num_timesteps"])
     np.savez_compressed(os.path.join(HERE, f"policy_{t}.npz"), **out)
     print(t, {k: (v.shape if getattr(v, "shape", ()) else float(v)) for k, v in out.items()})

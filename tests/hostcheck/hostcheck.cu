@@ -144,6 +144,18 @@ void hc_ee_pose(int64_t n, const float *q, float *ee) {
         robot_pass<TASK_ORI, GEOM_CAPSULE>(g_M, q + i * 6, q + i * 6, O, nullptr, false, ee + i * 6, du, nullptr, 1);
     }
 }
+// experiments (tools/closed_loop_cpu.py): shift a scene box along z. box 0 = table, 1 = track
+void hc_shift_box_z(int box, float dz) {
+    init();
+    g_M.box_c[box][2] += dz;
+    for (int l = 0; l < 7; l++) g_M.box_lim[l][box][0] += dz;
+}
+// experiments: obstacle cylinder core radius / half height / margin
+void hc_set_obstacle(float r, float h, float margin) {
+    init();
+    g_M.obst_r = r; g_M.obst_h = h; g_M.obst_margin = margin;
+}
+void hc_set_ld_mode(int mode) { init(); g_M.ld_mode = mode; }
 void hc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
     uint4 r = philox4x32_10(make_uint4(c[0], c[1], c[2], c[3]), make_uint2(k[0], k[1]));
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;

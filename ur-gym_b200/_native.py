@@ -13,6 +13,8 @@ TASK_IDS = {"UR5OriReach-v1": 0, "UR5ObsReach-v1": 1, "UR5StaReach-v1": 2, "UR5D
 GEOM_HULL, GEOM_CAPSULE = 0, 1
 GEOMS = {"hull": GEOM_HULL, "capsule": GEOM_CAPSULE}
 (F_Q, F_GOAL, F_OBSTACLE, F_OBSTACLE_END, F_LINK_DIST, F_ELAPSED, F_EP_RETURN, F_VELOCITY, F_HOT) = range(9)
+LD_OBSTACLE, LD_WORKBENCH = 0, 1
+LINK_DIST_MODES = {"obstacle": LD_OBSTACLE, "workbench": LD_WORKBENCH}
 STATS_COUNT = 8
 STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions", "truncations", "env_steps",
               "reset_iterations")
@@ -20,7 +22,7 @@ STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions",
 EXPORTS = ["urgym_step_range", "urgym_create", "urgym_destroy", "urgym_last_error", "urgym_obs_dim", "urgym_goal_dim", "urgym_num_envs",
            "urgym_step", "urgym_reset", "urgym_observe", "urgym_refresh", "urgym_get_state", "urgym_set_state",
            "urgym_stats", "urgym_step_host", "urgym_reset_host", "urgym_set_autoreset", "urgym_get_event",
-           "urgym_set_event", "urgym_set_seed", "urgym_launch_count", "urgym_profile_enable", "urgym_profile_read"]
+           "urgym_set_event", "urgym_set_seed", "urgym_set_link_dist_mode", "urgym_launch_count", "urgym_profile_enable", "urgym_profile_read"]
 
 
 class UrgymError(RuntimeError):
@@ -57,6 +59,7 @@ def lib():
         L.urgym_get_event.argtypes = [vp, ctypes.POINTER(u32)]
         L.urgym_set_event.argtypes = [vp, u32]
         L.urgym_set_seed.argtypes = [vp, u64]
+        L.urgym_set_link_dist_mode.argtypes = [vp, i32]
         L.urgym_launch_count.argtypes = [vp]; L.urgym_launch_count.restype = i64
         L.urgym_profile_enable.argtypes = [vp, i32]
         L.urgym_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]

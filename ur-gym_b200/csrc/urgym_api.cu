@@ -250,6 +250,13 @@ extern "C" int urgym_set_autoreset(urgym_env_t *h, int enabled) {
     h->autoreset = enabled ? 1 : 0;
     return URGYM_OK;
 }
+extern "C" int urgym_set_link_dist_mode(urgym_env_t *h, int mode) {
+    if (!h) return URGYM_EINVAL;
+    if (mode != URGYM_LD_OBSTACLE && mode != URGYM_LD_WORKBENCH) return fail(h, URGYM_EINVAL, "urgym_set_link_dist_mode: unknown mode%s", "");
+    if (h->task == 0) return fail(h, URGYM_EUNSUPPORTED, "urgym_set_link_dist_mode: UR5OriReach has no link_dist%s", "");
+    h->model.ld_mode = mode;        // the model constants travel with every launch (__grid_constant__)
+    return URGYM_OK;
+}
 extern "C" int urgym_set_seed(urgym_env_t *h, uint64_t seed) {
     if (!h) return URGYM_EINVAL;
     h->seed = seed;

@@ -234,6 +234,12 @@ template <> struct LinkShape<GEOM_CAPSULE> {
         float3 oa = O.c - M.fit_obst_h * O.u, ob = O.c + M.fit_obst_h * O.u;
         return sqrtf(segseg_dist2(a, b, oa, ob)) - M.fit_obst[l];
     }
+    // getClosestPoints(UR5, table | track, linkIndexA=l)[0][8], capsule geometry (link-distance mode "workbench")
+    URGYM_HD float box_dist(const ModelConst &M, int l, int box) const {
+        float3 bc = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
+        float3 bh = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
+        return sqrtf(seg_box_dist2(a, b, bc, bh)) - M.fit_box[l] - M.box_margin[box];
+    }
     // the methods below use the BOUNDING capsules: they are the exact-safe broad phase of the hull geometry
     // box 0 = table, 1 = track
     URGYM_HD bool box_hit(const ModelConst &M, int l, int box) const {
@@ -287,6 +293,12 @@ template <> struct LinkShape<GEOM_HULL> {
         CylW C; C.c = O.c; C.u = O.u; C.r = M.obst_r; C.h = M.obst_h;      // end caps / rims / penetration
         float d = gjk_distance(hull(M, l), C, deep);
         return d - M.hull_margin - M.obst_margin;
+    }
+    URGYM_HD float box_dist(const ModelConst &M, int l, int box) const {      // link-distance mode "workbench"
+        BoxA B; B.c = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
+        B.he = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
+        bool deep;
+        return gjk_distance(hull(M, l), B, deep) - M.hull_margin - M.box_margin[box];
     }
     URGYM_HD bool box_hit(const ModelConst &M, int l, int box) const {
         if (!cap.box_hit(M, l, box)) return false;
@@ -343,6 +355,7 @@ URGYM_HD bool robot_pass_rolled(const ModelConst &M, const float *qrow, const Ob
                 if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
                     float d = cur.obstacle_dist(M, l, O);
                     hit = hit || (d <= URGYM_COLLISION_MARGIN);
+                    if (M.ld_mode) d = fminf(d, fminf(cur.box_dist(M, l, 0), cur.box_dist(M, l, 1)));
                     if (l == 2) d0 = d; else if (l == 3) d1 = d; else if (l == 4) d2 = d; else if (l == 5) d3 = d; else d4 = d;
                 }
 #pragma unroll 1
@@ -365,6 +378,18 @@ URGYM_HD bool robot_pass_rolled(const ModelConst &M, const float *qrow, const Ob
 // link pairs, so each distance routine exists once in the instruction stream.
 // scratch layout: 36 floats capsule endpoints (link 1..6: a.xyz b.xyz), 5 floats link-obstacle distances.
 #define URGYM_SCRATCH_FLOATS 41
+// link-distance mode "workbench": fold the link's distances to the table and the track into the link-obstacle
+// distances of the scratch column.  Out of line and behind a warp-uniform branch: the default mode pays two instructions.
+static URGYM_OOL void workbench_link_dist(const ModelConst &M, float *cap, int cs) {
+#pragma unroll 1
+    for (int l = 2; l < 7; l++) {
+        const float *c = cap + (l - 1) * 6 * cs;
+        LinkShape<GEOM_CAPSULE> L;
+        L.a = f3(c[0], c[cs], c[2 * cs]); L.b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
+        float &d = cap[(36 + l - 2) * cs];
+        d = fminf(d, fminf(L.box_dist(M, l, 0), L.box_dist(M, l, 1)));
+    }
+}
 template <int TASK>
 URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const ObstW &O, bool collide, float *ee,
                                  float *dist, float *cap, int cs) {
@@ -473,6 +498,7 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
         }
     }
     if (Traits<TASK>::HAS_OBST) {
+        if (M.ld_mode) workbench_link_dist(M, cap, cs);
 #pragma unroll
         for (int k = 0; k < 5; k++) dist[k] = cap[(36 + k) * cs];
     }
@@ -747,6 +773,7 @@ URGYM_HD int env_reset(const ModelConst &M, EnvState &s, ResetStream rs, const f
             LinkShape<GEOM> L;
             L.set_neutral(M, l, hv);
             float d = L.obstacle_dist(M, l, O);
+            if (M.ld_mode) d = fminf(d, fminf(L.box_dist(M, l, 0), L.box_dist(M, l, 1)));
             if (l == 2) s.ld[0] = d; else if (l == 3) s.ld[1] = d; else if (l == 4) s.ld[2] = d; else if (l == 5) s.ld[3] = d; else s.ld[4] = d;
         }
     } else {

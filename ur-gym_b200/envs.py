@@ -172,12 +172,12 @@ class RobotTaskEnv:
     metadata = {"render_modes": ["human", "rgb_array"]}
 
     def __init__(self, env_id: str, render: bool = False, device: int = 0, seed: Optional[int] = None,
-                 geometry: str = "capsule", env_index: int = 0):
+                 geometry: str = "capsule", env_index: int = 0, link_dist: str = "obstacle"):
         if render:
             raise NotImplementedError("the batched GPU simulator has no GUI; use render=False")
         self.spec = _Spec(env_id)
         self.vec = UR5VecEnv(env_id, 1, device=device, seed=0 if seed is None else seed, env_index_offset=env_index,
-                             geometry=geometry, auto_reset=False)
+                             geometry=geometry, auto_reset=False, link_dist=link_dist)
         self.robot, self.task = Robot(self), Task(self)
         self.sim = self.vec
         self._ld_prev = self._ld_new = np.zeros(5)

@@ -22,14 +22,20 @@ class UR5VecEnv:
     [env_index_offset, env_index_offset + num_envs).
 
     geometry: "capsule" (bounding capsules, closed-form distances: the throughput path) or "hull" (the reference's
-    convex-hull link meshes and cylinder obstacle through GJK: the reference-geometry path)."""
+    convex-hull link meshes and cylinder obstacle through GJK: the reference-geometry path).
+    link_dist: what the `link_dist` observation columns and reward term measure -- "obstacle" (links vs the obstacle,
+    pyb_setup.py:439-456 as shipped; default) or "workbench" (per link the smallest distance to obstacle, table and
+    track: the method's docstring, and the definition the shipped Obs / Sta policies were trained with)."""
 
     def __init__(self, env_id: str, num_envs: int, device: int = 0, seed: int = 0, env_index_offset: int = 0,
-                 geometry: str = "capsule", auto_reset: bool = True, goal_buffers: bool = False):
+                 geometry: str = "capsule", auto_reset: bool = True, goal_buffers: bool = False,
+                 link_dist: str = "obstacle"):
         if env_id not in nat.TASK_IDS:
             raise ValueError(f"unknown env id {env_id!r}; known: {sorted(nat.TASK_IDS)}")
         if geometry not in nat.GEOMS:
             raise ValueError("geometry must be 'capsule' or 'hull'")
+        if link_dist not in nat.LINK_DIST_MODES:
+            raise ValueError("link_dist must be 'obstacle' or 'workbench'")
         if not torch.cuda.is_available():
             raise nat.UrgymError("no CUDA device: ur-gym_b200 has no CPU path")
         self.env_id, self.task = env_id, nat.TASK_IDS[env_id]
@@ -44,6 +50,9 @@ class UR5VecEnv:
         self.h = h
         if not auto_reset:
             nat.check(self.h, self.L.urgym_set_autoreset(self.h, 0))
+        self.link_dist_mode = link_dist
+        if link_dist != "obstacle" and self.task != 0:
+            nat.check(self.h, self.L.urgym_set_link_dist_mode(self.h, nat.LINK_DIST_MODES[link_dist]))
         n, D, G = self.num_envs, self.obs_dim, self.goal_dim
         kw = dict(device=self.device)
         self.obs = torch.zeros((n, D), dtype=torch.float32, **kw)
