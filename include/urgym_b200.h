@@ -52,7 +52,8 @@ enum { URGYM_LD_OBSTACLE = 0,   /* links 2..6 vs the obstacle: the code the refe
 enum { URGYM_F_Q = 0,            /* float [N,6]  joint angles                                  */
        URGYM_F_GOAL = 1,         /* float [N,G]  goal (pos[,euler]); G = urgym_goal_dim()      */
        URGYM_F_OBSTACLE = 2,     /* float [N,6]  obstacle pose pos+euler (Dyn: obstacle_start) */
-       URGYM_F_OBSTACLE_END = 3, /* float [N,6]  Dyn obstacle_end                              */
+       URGYM_F_OBSTACLE_END = 3, /* float [N,6]  obstacle_end: Dyn (reach.py:670), Sta (18-value injection, reach.py:491-499;
+                                    all zero = obstacle at rest, core.py:307-308)                     */
        URGYM_F_LINK_DIST = 4,    /* float [N,5]  link_dist == last_dist (reach.py:324,479,681) */
        URGYM_F_ELAPSED = 5,      /* int32 [N]    TimeLimit counter == ReachDyn.step_num        */
        URGYM_F_EP_RETURN = 6,    /* float [N]    running episode return                        */
@@ -60,7 +61,9 @@ enum { URGYM_F_Q = 0,            /* float [N,6]  joint angles                   
        URGYM_F_HOT = 8,          /* float [N,24] the step kernel's copy of the episode constants + episode cache (derived
                                     from GOAL / OBSTACLE / OBSTACLE_END whenever those are set; raw words, for
                                     checkpoints: restoring it after the other fields makes a restore bit-exact) */
-       URGYM_F_COUNT = 9 };
+       URGYM_F_OBSTACLE_START = 9, /* float [N,6] Sta: ReachSta.obstacle_start (reach.py:493; the twist of the moving obstacle
+                                    is (end - start) / 1 s, reach.py:518-541); Dyn: alias of URGYM_F_OBSTACLE  */
+       URGYM_F_COUNT = 10 };
 
 #define URGYM_OK 0
 #define URGYM_EINVAL (-1)     /* bad argument                         */
@@ -155,8 +158,13 @@ int urgym_set_autoreset(urgym_env_t *h, int enabled);
 /* URGYM_LD_*; takes effect with the next launch: call urgym_refresh afterwards so that link_dist = last_dist are
  * re-measured in the new mode.  URGYM_EUNSUPPORTED for UR5OriReach (no obstacle, no link_dist). */
 int urgym_set_link_dist_mode(urgym_env_t *h, int mode);
-/* the reset-event counter (position of the reset stream); together with the URGYM_F_* fields it checkpoints a handle */
+/* the reset-event counter (position of the reset stream; the largest of the chains' counters); together with the
+ * URGYM_F_* fields it checkpoints a handle.  urgym_set_event sets every chain's counter. */
 int urgym_get_event(const urgym_env_t *h, uint32_t *event);
+/* Raise every chain's reset-event counter to the largest of them (stream-ordered, one tiny kernel).  To be enqueued before
+ * a group of urgym_step_range calls whenever the chains may have been stepped unequally before (a different chain layout,
+ * a graph with fewer chains): afterwards no chain can draw from a reset-stream position that was already used. */
+int urgym_sync_events(urgym_env_t *h, void *stream);
 /* re-key the reset stream: RobotTaskEnv.reset(seed=...) re-creates task.np_random (core.py:267) */
 int urgym_set_seed(urgym_env_t *h, uint64_t seed);
 int urgym_set_event(urgym_env_t *h, uint32_t event);

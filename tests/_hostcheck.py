@@ -34,7 +34,7 @@ class HostCheckSim:
         self.link_dist_mode = link_dist_mode
         self.D, self.G = OBS_DIM[self.task], GOAL_DIM[self.task]
         self.q = np.zeros((n, 6), np.float32); self.elapsed = np.zeros(n, np.int32); self.ep_ret = np.zeros(n, np.float32)
-        self.ld = np.zeros((n, 5), np.float32); self.E = np.zeros((n, 18), np.float32)
+        self.ld = np.zeros((n, 5), np.float32); self.E = np.zeros((n, 24), np.float32)
         self.stale_vel = np.zeros((n, 6), np.float32)
         self.event = 0
         self.autoreset = autoreset
@@ -48,7 +48,7 @@ class HostCheckSim:
         """reset envs `rows`; obs rows must already hold the velocity columns to keep (quirk Q4)"""
         m = len(rows)
         q = np.zeros((m, 6), np.float32); el = np.zeros(m, np.int32); er = np.zeros(m, np.float32)
-        ld = np.zeros((m, 5), np.float32); E = np.zeros((m, 18), np.float32)
+        ld = np.zeros((m, 5), np.float32); E = np.ascontiguousarray(self.E[rows])
         o = np.ascontiguousarray(obs[rows]); it = np.zeros(m, np.int32)
         env_index = (np.asarray(rows, np.int64) + self.offset).astype(np.int64)
         rc = self.L.hc_reset(self.task, self.geom, ctypes.c_int64(m), _p(q), _p(el), _p(er), _p(ld), _p(E),
@@ -111,6 +111,9 @@ class HostCheckSim:
 
     def set_obstacle_end(self, o):
         self.E[:, 12:18] = o
+
+    def set_obstacle_start(self, o):            # ReachSta only (Dyn's start is set_obstacle)
+        self.E[:, 18:24] = o
 
 
 def ee_pose(q):

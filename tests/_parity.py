@@ -11,7 +11,7 @@ POS_TOL = 1e-5        # m
 ANG_TOL = 1e-5        # rad
 REW_RTOL = 1e-5
 Q_TOL = 1e-3
-THRESH_EPS = 2e-6     # booleans may differ only when the deciding quantity is this close to its threshold
+THRESH_EPS = 1e-6     # booleans may differ only when the deciding quantity is this close to its threshold (north_star)
 EULER_COLS = {"UR5OriReach-v1": [3, 4, 5, 15, 16, 17], "UR5ObsReach-v1": [3, 4, 5],
               "UR5StaReach-v1": [3, 4, 5, 15, 16, 17, 21, 22, 23], "UR5DynReach-v1": [3, 4, 5, 15, 16, 17, 21, 22, 23]}
 
@@ -65,11 +65,13 @@ def obs_close(env_id, got, want, ld_tol=None):
 
 
 class OracleBatch:
-    def __init__(self, env_id, geom, n, seed, offset=0, first_event=1, link_dist_mode=0):
+    def __init__(self, env_id, geom, n, seed, offset=0, first_event=1, link_dist_mode=0, indices=None):
         self.env_id = env_id
-        self.envs = [oe.make(env_id, geom=geom, stream=oe.PhiloxStream(seed), env_index=offset + i, first_event=first_event,
+        idx = [offset + i for i in range(n)] if indices is None else [int(i) for i in indices]
+        assert len(idx) == n
+        self.envs = [oe.make(env_id, geom=geom, stream=oe.PhiloxStream(seed), env_index=g, first_event=first_event,
                              link_dist_mode=link_dist_mode)
-                     for i in range(n)]
+                     for g in idx]
 
     def first_obs(self):
         return np.stack([e._get_obs()["observation"] for e in self.envs])
@@ -87,10 +89,26 @@ class OracleBatch:
         return min(m)
 
 
+def sta_moving_scenarios(n, seed):
+    """18-value ReachSta scenarios (goal, obstacle_start, obstacle_end; reach.py:491-499) with start-end distances from
+    0.02 m (never moves: already within 0.05 m) to ~0.7 m"""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, 18), np.float32)
+    for i in range(n):
+        goal = np.concatenate([rng.uniform([0.3, -0.5, 0.0], [0.75, 0.5, 0.2]), oe.euler_constrained_from_uniform(rng.random(), rng.random())])
+        start = np.concatenate([rng.uniform([0.5, -0.5, 0.25], [1.0, 0.5, 0.55]), oe.euler_obstacle_from_uniform(*rng.random(3))])
+        end = np.concatenate([rng.uniform([0.5, -0.5, 0.25], [1.0, 0.5, 0.55]), oe.euler_obstacle_from_uniform(*rng.random(3))])
+        if i % 6 == 0:          # a short hop: the obstacle never leaves the 0.05 m ball around its end point
+            end[:3] = start[:3] + rng.uniform(-0.02, 0.02, 3)
+        out[i] = np.concatenate([goal, start, end])
+    return out
+
+
 def run_parity(sim, env_id, geom, n, steps, seed, offset=0, action_scale=1.2, rng_seed=0, check_terminal=True,
-               ld_tol=None, rew_atol=0.0, link_dist_mode=0):
-    """sim: .reset() -> obs [n,D]; .step(a) -> dict(obs, reward, terminated, truncated, is_success, terminal_obs)."""
-    orc = OracleBatch(env_id, geom, n, seed, offset, first_event=1, link_dist_mode=link_dist_mode)
+               ld_tol=None, rew_atol=0.0, link_dist_mode=0, after_reset=None, indices=None):
+    """sim: .reset() -> obs [n,D]; .step(a) -> dict(obs, reward, terminated, truncated, is_success, terminal_obs).
+    indices: GLOBAL env indices of the n rows `sim` exposes (default offset .. offset + n - 1)."""
+    orc = OracleBatch(env_id, geom, n, seed, offset, first_event=1, link_dist_mode=link_dist_mode, indices=indices)
     obs = sim.reset()
     event = 1
     alive = np.ones(n, bool)
@@ -98,12 +116,14 @@ def run_parity(sim, env_id, geom, n, steps, seed, offset=0, action_scale=1.2, rn
         if e.task.kind != "Ori" and e.task.min_reject_margin < 1e-5:
             alive[i] = False
     want = orc.first_obs()
-    stats = dict(max_lin=0.0, max_ang=0.0, max_rew_rel=0.0, max_q=0.0, steps=0, resets=0, dropped=0, bool_exempt=0,
-                 collisions=0, successes=0, truncations=0)
+    stats = dict(max_lin=0.0, max_ang=0.0, max_rew_rel=0.0, max_rew_rel_strict=0.0, rew_cancellation_exempt=0, max_q=0.0,
+                 steps=0, resets=0, dropped=0, bool_exempt=0, collisions=0, successes=0, truncations=0)
     for i in range(n):
         if alive[i]:
             lin, ang = obs_close(env_id, obs[i], want[i], ld_tol)
             assert lin <= POS_TOL and ang <= ANG_TOL, ("first obs", i, lin, ang)
+    if after_reset is not None:         # scenario injection into both sides (model_test.py:34-38)
+        after_reset(sim, orc)
     rng = np.random.default_rng(rng_seed)
     for t in range(steps):
         a = (rng.uniform(-1, 1, (n, 6)) * action_scale).astype(np.float32)
@@ -131,11 +151,19 @@ def run_parity(sim, env_id, geom, n, steps, seed, offset=0, action_scale=1.2, rn
                 assert lin <= POS_TOL and ang <= ANG_TOL, ("obs", env_id, i, t, lin, ang, got_obs, o["observation"])
                 stats["max_lin"], stats["max_ang"] = max(stats["max_lin"], lin), max(stats["max_ang"], ang)
                 stats["max_q"] = max(stats["max_q"], np.abs(got_obs[6:12] - o["observation"][6:12]).max())
-            # 1e-5 relative to the size of the reward's TERMS: -100 d (Obs) / -70 d - 30 ang and w_i * (link_dist change)
-            # partly cancel, so a reward of -7 can be the difference of terms of size 50
+            # north_star: |dr| <= 1e-5 * max(1, |r|).  The reward is a sum of terms that partly cancel (-100 d (Obs) /
+            # -70 d - 30 ang against w_i * (link_dist change)): an FP32 result can miss the strict bound when |r| is much
+            # smaller than its terms.  Those steps are COUNTED (rew_cancellation_exempt) and must still meet 1e-5 relative
+            # to the size of the terms; everything else is held to the strict bound.
+            err = max(0.0, abs(float(out["reward"][i]) - r) - rew_atol)
+            strict = err / max(1.0, abs(r))
             scale = max(1.0, abs(r), 100.0 * float(oe.distance(o["achieved_goal"], e.task.get_goal())[0])
                         + 100.0 * float(np.abs(np.asarray(e.task.link_dist) - ld_before).sum()))
-            rel = max(0.0, abs(float(out["reward"][i]) - r) - rew_atol) / scale
+            rel = err / scale
+            if strict > REW_RTOL and rel <= REW_RTOL:
+                stats["rew_cancellation_exempt"] += 1
+            else:
+                stats["max_rew_rel_strict"] = max(stats["max_rew_rel_strict"], min(strict, rel if rel > REW_RTOL else strict))
             if rel > REW_RTOL and not (e.task.kind == "Obs" and getattr(e.sim, "last_deep_mask", 0)):
                 # (Obs keeps the link-distance term on a colliding step; with interpenetrating cores the oracle's
                 # distance is a placeholder -- Bullet would run EPA there -- so that reward is not compared)
@@ -156,4 +184,6 @@ def run_parity(sim, env_id, geom, n, steps, seed, offset=0, action_scale=1.2, rn
                 lin, ang = obs_close(env_id, out["obs"][i], o2["observation"], ld_tol)
                 assert lin <= POS_TOL and ang <= ANG_TOL, ("reset obs", env_id, i, t, lin, ang, out["obs"][i], o2["observation"])
     assert stats["max_q"] <= Q_TOL
+    # the cancellation exemption stays an exception: well under 1 % of the compared steps
+    assert stats["rew_cancellation_exempt"] <= 0.01 * max(stats["steps"], 1) + 2, stats
     return stats

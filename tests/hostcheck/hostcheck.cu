@@ -30,19 +30,19 @@ struct HcState {        // mirrors EnvState, API layout
     int32_t *elapsed;   // [n]
     float *ep_ret;      // [n]
     float *ld;          // [n,5]
-    float *E;           // [n,18] (first EW words used)
+    float *E;           // [n,24] (first EW words used)
 };
 static void get(const HcState &S, int64_t i, EnvState &s) {
     for (int k = 0; k < 6; k++) s.q[k] = S.q[i * 6 + k];
     s.elapsed = S.elapsed[i]; s.ep_ret = S.ep_ret[i];
     for (int k = 0; k < 5; k++) s.ld[k] = S.ld[i * 5 + k];
-    for (int k = 0; k < 18; k++) s.E[k] = S.E[i * 18 + k];
+    for (int k = 0; k < 24; k++) s.E[k] = S.E[i * 24 + k];
 }
 static void put(const HcState &S, int64_t i, const EnvState &s) {
     for (int k = 0; k < 6; k++) S.q[i * 6 + k] = s.q[k];
     S.elapsed[i] = s.elapsed; S.ep_ret[i] = s.ep_ret;
     for (int k = 0; k < 5; k++) S.ld[i * 5 + k] = s.ld[k];
-    for (int k = 0; k < 18; k++) S.E[i * 18 + k] = s.E[k];
+    for (int k = 0; k < 24; k++) S.E[i * 24 + k] = s.E[k];
 }
 
 template <int TASK, int GEOM>
@@ -65,6 +65,7 @@ static void reset_t(int64_t n, HcState S, uint64_t seed, uint32_t event, const i
     constexpr int D = Traits<TASK>::OBS;
     for (int64_t i = 0; i < n; i++) {
         EnvState s;
+        get(S, i, s);           // ReachSta keeps obstacle_end / obstacle_start over a reset
         ResetStream rs;
         rs.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)); rs.episode = event;
         rs.env_lo = (uint32_t)env_index[i]; rs.env_hi = (uint32_t)((uint64_t)env_index[i] >> 32);

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import oracle_env as oe
-from tests._parity import obs_close, run_parity
+from tests._parity import obs_close, run_parity, sta_moving_scenarios
 
 pytestmark = pytest.mark.gpu
 TASKS = ["UR5OriReach-v1", "UR5ObsReach-v1", "UR5StaReach-v1", "UR5DynReach-v1"]
@@ -416,3 +416,127 @@ def test_sb3_style_vec_env_contract(ug):
         assert all("terminal_observation" not in infos[i] for i in np.nonzero(~dones)[0][:20])
     assert seen_done > 0 and seen_trunc > 0
     venv.close()
+
+
+# ---------------------------------------------------------------------------------------------------- round 2
+@pytest.mark.parametrize("env_id,n_total,shard", [("UR5DynReach-v1", 1 << 20, None), ("UR5ObsReach-v1", 1 << 20, None),
+                                                  ("UR5OriReach-v1", 65536, None), ("UR5StaReach-v1", 1 << 21, 1)])
+def test_full_size_oracle_sample(env_id, n_total, shard, ug):
+    """Oracle parity AT the sizes BASELINE.json names (C5 per GPU, C3, C2, and the second 2 Mi shard of C4's 4 Mi envs):
+    2 048 global env indices spread over the whole batch, one oracle env per index (the reset stream is keyed by the
+    global index), 30 steps with auto-reset, every observation / reward / flag / terminal row / post-reset row compared
+    at the north-star tolerances while the other envs of the batch step alongside."""
+    from tests._gpu import GpuSampleSim
+    offset = 0 if shard is None else shard * n_total
+    rng = np.random.default_rng(17)
+    k = 2048
+    # whole tiles' first / last rows, the batch's first and last env, and a uniform sample
+    fixed = [0, 1, 31, 32, 127, 128, n_total - 1, n_total - 2, n_total - 129]
+    idx = np.unique(np.concatenate([fixed, rng.choice(n_total, k - len(fixed), replace=False)]))[:k] + offset
+    sim = GpuSampleSim(env_id, n_total, idx, seed=31, offset=offset)
+    st = run_parity(sim, env_id, oe.GEOM_CAPSULE, len(idx), 30, seed=31, indices=idx)
+    assert st["steps"] > 0.9 * len(idx) * 30 and st["resets"] > 0, st
+    print(env_id, n_total, st)
+
+
+@pytest.mark.parametrize("env_id", ["UR5ObsReach-v1", "UR5StaReach-v1", "UR5DynReach-v1"])
+def test_workbench_link_dist_mode_parity(env_id, ug):
+    from tests._gpu import GpuSim
+    n, steps = 200, 60
+    st = run_parity(GpuSim(env_id, oe.GEOM_CAPSULE, n, seed=21, offset=300, link_dist_mode=oe.LD_WORKBENCH), env_id,
+                    oe.GEOM_CAPSULE, n, steps, seed=21, offset=300, link_dist_mode=oe.LD_WORKBENCH)
+    assert st["steps"] > 0.85 * n * steps and st["resets"] > 0, st
+    # and the mode is what it says: never larger than the obstacle-only distance, smaller for links near the table
+    a = ug.UR5VecEnv(env_id, 4096, seed=5, link_dist="workbench"); b = ug.UR5VecEnv(env_id, 4096, seed=5)
+    a.reset(); b.reset()
+    la, lb = a.get_state("link_dist"), b.get_state("link_dist")
+    assert (la <= lb + 1e-7).all() and (la < lb - 1e-3).any()
+
+
+@pytest.mark.parametrize("geom", [oe.GEOM_CAPSULE, oe.GEOM_HULL])
+def test_sta_moving_obstacle_injection(geom, ug):
+    """ReachSta's 18-value injection (reach.py:483-503) + set_velocity (reach.py:518-541) through urgym_set_state"""
+    from tests._gpu import GpuSim
+    n, steps = (200, 70) if geom == oe.GEOM_CAPSULE else (40, 35)
+    sc = sta_moving_scenarios(n, seed=5)
+
+    def inject(sim, orc):
+        sim.set_goal(sc[:, :6]); sim.set_obstacle(sc[:, 6:12]); sim.set_obstacle_start(sc[:, 6:12]); sim.set_obstacle_end(sc[:, 12:])
+        sim.refresh()
+        for i, e in enumerate(orc.envs):
+            e.task.set_goal_and_obstacle(sc[i].astype(np.float64))
+
+    kw = dict(ld_tol=5e-5, rew_atol=1e-2) if geom == oe.GEOM_HULL else {}
+    st = run_parity(GpuSim("UR5StaReach-v1", geom, n, seed=8, offset=40), "UR5StaReach-v1", geom, n, steps, seed=8, offset=40,
+                    action_scale=0.6, after_reset=inject, **kw)
+    assert st["steps"] > 0.8 * n * steps and st["resets"] > 0, st
+
+
+def test_sta_moving_obstacle_through_make(ug):
+    """the reference-facing surface: env.task.set_goal_and_obstacle(18 values) on make('UR5StaReach-v1')"""
+    env = ug.make("UR5StaReach-v1", seed=0)
+    orc = oe.make("UR5StaReach-v1", geom=oe.GEOM_CAPSULE, stream=oe.PhiloxStream(0), env_index=0, first_event=1)
+    env.reset(); orc.reset(event=2)
+    data = np.array([0.5, 0.1, 0.1, -2.0, 0.0, -1.0, 0.6, -0.4, 0.3, 1.0, 0.8, 0.0, 0.9, 0.4, 0.5, -2.0, -1.2, 0.0])
+    env.task.set_goal_and_obstacle(data); orc.task.set_goal_and_obstacle(data)
+    np.testing.assert_allclose(env.task.obstacle_end, data[12:], atol=1e-6)
+    np.testing.assert_allclose(env.task.obstacle_start, data[6:12], atol=1e-6)
+    rng = np.random.default_rng(1)
+    moved = 0.0
+    for t in range(40):
+        a = rng.uniform(-0.2, 0.2, 6).astype(np.float32)
+        o, r, term, trunc, info = env.step(a)
+        o2, r2, term2, trunc2, info2 = orc.step(a)
+        lin, ang = obs_close("UR5StaReach-v1", o["observation"], o2["observation"])
+        assert lin <= 1e-5 and ang <= 1e-5, (t, lin, ang)
+        assert abs(r - r2) <= 1e-5 * max(1.0, abs(r2)) and term == term2
+        moved = max(moved, float(np.linalg.norm(o["observation"][18:21] - data[6:9])))
+        if term:
+            break
+    assert moved > 0.5          # the obstacle travelled to (within 0.05 m of) its end point
+    with pytest.raises(ValueError):
+        env.task.set_goal_and_obstacle(np.zeros(7))
+    env.close()
+
+
+def test_use_before_reset_raises_and_checkpoint_is_validated(ug):
+    env = ug.UR5VecEnv("UR5DynReach-v1", 64, seed=1)
+    with pytest.raises(ug.UrgymError):
+        env.step(torch.zeros((64, 6), device="cuda"))
+    with pytest.raises(ug.UrgymError):
+        env.observe()
+    env.reset()
+    ck = env.state_dict()
+    other = ug.UR5VecEnv("UR5DynReach-v1", 64, seed=2)
+    with pytest.raises(ug.UrgymError):
+        other.load_state_dict(ck)                       # another seed: the reset stream would differ
+    shuffled = dict(reversed(list(ck.items())))         # the dict's own order does not matter
+    same = ug.UR5VecEnv("UR5DynReach-v1", 64, seed=1)
+    same.load_state_dict(shuffled)
+    a = torch.rand((64, 6), device="cuda") * 2 - 1
+    assert torch.equal(env.step(a)[0]["observation"], same.step(a)[0]["observation"])
+
+
+def test_chain_layout_change_never_reuses_reset_stream_positions(ug):
+    """2-chain graph, then a 4-chain graph of the same handle: urgym_sync_events at the head of every chained graph
+    raises the lagging chains' counters, so the second layout draws fresh episodes."""
+    env_id, n, k = "UR5DynReach-v1", 40_000, 5
+    env = ug.UR5VecEnv(env_id, n, seed=3); env.reset()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    ring = [torch.rand((n, 6), device="cuda", generator=g) * 2.4 - 1.2 for _ in range(k)]
+    g2 = env.capture_steps(ring, chains=2)
+    for _ in range(3):
+        g2.replay()
+    torch.cuda.synchronize()
+    ev = ctypes.c_uint32(); env.L.urgym_get_event(env.h, ctypes.byref(ev))
+    assert ev.value == 1 + 3 * k
+    g4 = env.capture_steps(ring, chains=4)
+    g4.replay(); torch.cuda.synchronize()
+    env.L.urgym_get_event(env.h, ctypes.byref(ev))
+    assert ev.value == 1 + 4 * k
+    # reference run: the same 20 steps as whole-batch steps
+    ref = ug.UR5VecEnv(env_id, n, seed=3); ref.reset()
+    for _ in range(4):
+        for a in ring:
+            ref.step(a)
+    assert torch.equal(ref.obs, env.obs) and torch.equal(ref.get_state("goal"), env.get_state("goal"))

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from tests._hostcheck import HostCheckSim, ee_pose, philox
-from tests._parity import run_parity
+from tests._parity import run_parity, sta_moving_scenarios
 from oracle import oracle_env as oe
 
 TASKS = ["UR5OriReach-v1", "UR5ObsReach-v1", "UR5StaReach-v1", "UR5DynReach-v1"]
@@ -70,3 +70,26 @@ def test_workbench_link_dist_mode_parity(env_id, geom):
     kw = dict(ld_tol=1e-4, rew_atol=1e-2) if geom == oe.GEOM_HULL else {}
     st = run_parity(sim, env_id, geom, n, steps, seed=21, offset=300, link_dist_mode=oe.LD_WORKBENCH, **kw)
     assert st["steps"] > 0.85 * n * steps, st
+
+
+@pytest.mark.parametrize("geom", [oe.GEOM_CAPSULE, oe.GEOM_HULL])
+def test_sta_moving_obstacle_injection(geom):
+    """ReachSta's 18-value set_goal_and_obstacle (reach.py:491-499) arms ReachSta.set_velocity (core.py:307-308,
+    reach.py:518-541): the obstacle moves with twist (end - start) / 1 s until it is within 0.05 m of obstacle_end.
+    obstacle_end / obstacle_start survive the resets that follow (reach.py:465-481 does not clear them), so the new
+    episodes' obstacles drift with the stale twist -- replicated, and compared with the oracle step by step."""
+    n, steps = (36, 60) if geom == oe.GEOM_CAPSULE else (8, 35)
+    sc = sta_moving_scenarios(n, seed=5)
+
+    def inject(sim, orc):
+        sim.set_goal(sc[:, :6]); sim.set_obstacle(sc[:, 6:12]); sim.set_obstacle_start(sc[:, 6:12]); sim.set_obstacle_end(sc[:, 12:])
+        sim.refresh()
+        for i, e in enumerate(orc.envs):
+            e.task.set_goal_and_obstacle(sc[i].astype(np.float64))
+
+    sim = HostCheckSim("UR5StaReach-v1", geom, n, seed=8, offset=40)
+    kw = dict(ld_tol=5e-5, rew_atol=1e-2) if geom == oe.GEOM_HULL else {}
+    st = run_parity(sim, "UR5StaReach-v1", geom, n, steps, seed=8, offset=40, action_scale=0.6, after_reset=inject, **kw)
+    assert st["steps"] > 0.8 * n * steps and (st["resets"] > 0 or geom == oe.GEOM_HULL), st
+    moved = np.linalg.norm(sim.E[:, 12:15] - sim.E[:, 6:9], axis=1)
+    assert (moved > 0.05).sum() > n // 2                  # most scenarios really moved (end far from start)

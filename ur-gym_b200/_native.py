@@ -7,12 +7,17 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("URGYM_B200_LIB") or os.path.join(_HERE, "liburgym_b200.so")   # override: A/B builds while tuning
+LIB_PATH = os.path.join(_HERE, "liburgym_b200.so")
+if os.environ.get("URGYM_B200_LIB"):       # A/B builds while tuning kernels (tools/kernel_time.py): never silent
+    LIB_PATH = os.environ["URGYM_B200_LIB"]
+    import sys as _sys
+    print(f"[urgym_b200] WARNING: URGYM_B200_LIB overrides the library under test: {LIB_PATH}", file=_sys.stderr)
 
 TASK_IDS = {"UR5OriReach-v1": 0, "UR5ObsReach-v1": 1, "UR5StaReach-v1": 2, "UR5DynReach-v1": 3}
 GEOM_HULL, GEOM_CAPSULE = 0, 1
 GEOMS = {"hull": GEOM_HULL, "capsule": GEOM_CAPSULE}
-(F_Q, F_GOAL, F_OBSTACLE, F_OBSTACLE_END, F_LINK_DIST, F_ELAPSED, F_EP_RETURN, F_VELOCITY, F_HOT) = range(9)
+(F_Q, F_GOAL, F_OBSTACLE, F_OBSTACLE_END, F_LINK_DIST, F_ELAPSED, F_EP_RETURN, F_VELOCITY, F_HOT,
+ F_OBSTACLE_START) = range(10)
 LD_OBSTACLE, LD_WORKBENCH = 0, 1
 LINK_DIST_MODES = {"obstacle": LD_OBSTACLE, "workbench": LD_WORKBENCH}
 STATS_COUNT = 8
@@ -22,7 +27,7 @@ STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions",
 EXPORTS = ["urgym_step_range", "urgym_create", "urgym_destroy", "urgym_last_error", "urgym_obs_dim", "urgym_goal_dim", "urgym_num_envs",
            "urgym_step", "urgym_reset", "urgym_observe", "urgym_refresh", "urgym_get_state", "urgym_set_state",
            "urgym_stats", "urgym_step_host", "urgym_reset_host", "urgym_set_autoreset", "urgym_get_event",
-           "urgym_set_event", "urgym_set_seed", "urgym_set_link_dist_mode", "urgym_launch_count", "urgym_profile_enable", "urgym_profile_read"]
+           "urgym_set_event", "urgym_set_seed", "urgym_set_link_dist_mode", "urgym_sync_events", "urgym_launch_count", "urgym_profile_enable", "urgym_profile_read"]
 
 
 class UrgymError(RuntimeError):
@@ -60,6 +65,7 @@ def lib():
         L.urgym_set_event.argtypes = [vp, u32]
         L.urgym_set_seed.argtypes = [vp, u64]
         L.urgym_set_link_dist_mode.argtypes = [vp, i32]
+        L.urgym_sync_events.argtypes = [vp, vp]
         L.urgym_launch_count.argtypes = [vp]; L.urgym_launch_count.restype = i64
         L.urgym_profile_enable.argtypes = [vp, i32]
         L.urgym_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]

@@ -51,6 +51,11 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_field_kernel(const FieldArg
     case URGYM_F_OBSTACLE_END:
         for (int k = 0; k < 6; k++) mv(e_word(A.st, A.task, i, 12 + k), x + i * 6 + k);
         break;
+    case URGYM_F_OBSTACLE_START: {      // Sta: its own words; Dyn: obstacle_start is what URGYM_F_OBSTACLE holds
+        const int off = A.task == TASK_STA ? 18 : 6;
+        for (int k = 0; k < 6; k++) mv(e_word(A.st, A.task, i, off + k), x + i * 6 + k);
+        break;
+    }
     case URGYM_F_LINK_DIST: {
         float *l = reinterpret_cast<float *>(&A.st.ld4[i]);
         for (int k = 0; k < 4; k++) mv(l + k, x + i * 5 + k);
@@ -250,6 +255,14 @@ extern "C" int urgym_set_autoreset(urgym_env_t *h, int enabled) {
     h->autoreset = enabled ? 1 : 0;
     return URGYM_OK;
 }
+extern "C" int urgym_sync_events(urgym_env_t *h, void *stream) {
+    if (!h) return URGYM_EINVAL;
+    CK(cudaSetDevice(h->device));
+    urgym_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_event, 0u);
+    CK(cudaGetLastError());
+    h->launches++;
+    return URGYM_OK;
+}
 extern "C" int urgym_set_link_dist_mode(urgym_env_t *h, int mode) {
     if (!h) return URGYM_EINVAL;
     if (mode != URGYM_LD_OBSTACLE && mode != URGYM_LD_WORKBENCH) return fail(h, URGYM_EINVAL, "urgym_set_link_dist_mode: unknown mode%s", "");
@@ -267,7 +280,11 @@ extern "C" int urgym_get_event(const urgym_env_t *hc, uint32_t *event) {
     if (!h || !event) return URGYM_EINVAL;
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(event, h->d_event, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    uint32_t all[URGYM_MAX_CHAINS];
+    CK(cudaMemcpy(all, h->d_event, sizeof(all), cudaMemcpyDeviceToHost));
+    uint32_t m = 0u;
+    for (int c = 0; c < URGYM_MAX_CHAINS; c++) m = all[c] > m ? all[c] : m;     // the logical event: chains may lag
+    *event = m;
     return URGYM_OK;
 }
 extern "C" int urgym_set_event(urgym_env_t *h, uint32_t event) {
@@ -382,7 +399,7 @@ extern "C" int urgym_reset(urgym_env_t *h, const uint8_t *mask, float *obs, floa
     memset(&A, 0, sizeof(A));
     A.st = h->st; A.n = h->n; A.offset = h->offset; A.key = key_of(h->seed);
     A.mask = mask; A.obs = obs; A.ach = achieved; A.des = desired; A.stats = h->stats; A.event = h->d_event; A.hull = h->hull;
-    urgym_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_event);       // an explicit reset is a reset event of its own
+    urgym_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d_event, 1u);       // an explicit reset is a reset event of its own
     CK(cudaGetLastError());
     h->launches++;
     CK(k_reset[h->geom][h->task](h->model, A, (cudaStream_t)stream));
@@ -416,7 +433,8 @@ static int field_ok(urgym_env *h, int field) {
     if (field < 0 || field >= URGYM_F_COUNT) return 0;
     if (field == URGYM_F_OBSTACLE && h->task == 0) return 0;
     if (field == URGYM_F_LINK_DIST && h->task == 0) return 0;
-    if ((field == URGYM_F_OBSTACLE_END || field == URGYM_F_VELOCITY) && h->task != 3) return 0;
+    if ((field == URGYM_F_OBSTACLE_END || field == URGYM_F_OBSTACLE_START) && h->task != 2 && h->task != 3) return 0;
+    if (field == URGYM_F_VELOCITY && h->task != 3) return 0;
     return 1;
 }
 static int field_io(urgym_env *h, int field, void *ext, int to_state, void *stream) {
@@ -429,7 +447,8 @@ static int field_io(urgym_env *h, int field, void *ext, int to_state, void *stre
     urgym_field_kernel<<<grid_for(h->n), URGYM_BLOCK, 0, (cudaStream_t)stream>>>(A);
     CK(cudaGetLastError());
     h->launches++;
-    if (to_state && (field == URGYM_F_GOAL || field == URGYM_F_OBSTACLE || field == URGYM_F_OBSTACLE_END)) {
+    if (to_state && (field == URGYM_F_GOAL || field == URGYM_F_OBSTACLE || field == URGYM_F_OBSTACLE_END ||
+                     field == URGYM_F_OBSTACLE_START)) {
         // the step reads the episode constants through the hot planes (with the episode cache): rebuild them
         AuxArgs D;
         memset(&D, 0, sizeof(D));
@@ -499,7 +518,7 @@ extern "C" int urgym_step_host(urgym_env_t *h, const float *actions, float *obs,
     int64_t chunk = ((N / 8 + 255) / 256) * 256;
     if (chunk < 65536) chunk = N;                       // small batches: one chunk
     cudaStream_t s0 = h->hstream;
-    urgym_bump_kernel<<<1, 1, 0, s0>>>(h->d_event);
+    urgym_bump_kernel<<<1, 1, 0, s0>>>(h->d_event, 1u);
     CK(cudaGetLastError());
     h->launches++;
     CK(cudaEventRecord(h->ev_fork, s0));

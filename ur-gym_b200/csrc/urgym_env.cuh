@@ -9,7 +9,10 @@
 //                                               UR_gym/pyb_setup.py:382-456
 // State words per env ("episode constants" E are rewritten only at reset):
 //   q[6], elapsed (TimeLimit counter == ReachDyn.step_num), ep_return, link_dist[5] (== last_dist), E[EW]
-//   E: Ori goal[6] | Obs goal[3] obstacle[6] | Sta goal[6] obstacle[6] | Dyn goal[6] obstacle_start[6] obstacle_end[6]
+//   E: Ori goal[6] | Obs goal[3] obstacle[6] | Sta goal[6] obstacle[6] obstacle_end[6] obstacle_start[6]
+//      | Dyn goal[6] obstacle_start[6] obstacle_end[6]
+//   (ReachSta.obstacle_end / obstacle_start are zero until an 18-value set_goal_and_obstacle sets them, reach.py:491-499,
+//    and are NOT cleared by reset, reach.py:465-481: the moving-obstacle path of core.py:307-308)
 #pragma once
 #include "urgym_device.cuh"
 
@@ -27,7 +30,8 @@ enum { GEOM_HULL = 0, GEOM_CAPSULE = 1 };
 // the episode constants only and are therefore computed once per episode, at reset, instead of once per step:
 //   Ori  C = goal quaternion[4]                                  (utils.py:48-54 applied to the goal)
 //   Obs  C = obstacle axis[3]
-//   Sta  C = goal quaternion[4], obstacle axis[3], obstacle Euler read-back[3]   (reach.py:455-457)
+//   Sta  C = goal quaternion[4], m, then  m == 0 (obstacle at rest): axis[3], Euler read-back[3]   (reach.py:455-457)
+//                                         m  > 0 (moving for m steps):  start quaternion[4], twist[6]  (reach.py:518-541)
 //   Dyn  C = goal quaternion[4], start quaternion[4], ReachDyn.velocity[6]       (reach.py:728-753)
 // The step kernel reads the "hot" words H = E[0..EH) ++ C[0..CW) from their own planes.
 template <int TASK> struct Traits;
@@ -40,7 +44,7 @@ template <> struct Traits<TASK_OBS> {
     static constexpr bool HAS_OBST = true, ORI = false, DYN = false;
 };
 template <> struct Traits<TASK_STA> {
-    static constexpr int OBS = 29, GOAL = 6, EW = 12, BPI = 3, OBST = 6, EH = 9, CW = 10;
+    static constexpr int OBS = 29, GOAL = 6, EW = 24, BPI = 3, OBST = 6, EH = 9, CW = 15;
     static constexpr bool HAS_OBST = true, ORI = true, DYN = false;
 };
 template <> struct Traits<TASK_DYN> {
@@ -64,8 +68,8 @@ struct EnvState {
     int elapsed;
     float ep_ret;
     float ld[5];
-    float E[18];
-    float C[14];        // episode cache (derive_cache)
+    float E[24];
+    float C[15];        // episode cache (derive_cache)
 };
 
 struct StepOut {
@@ -98,7 +102,8 @@ URGYM_HD ObstW obstacle_static(const float *o) {      // set_base_pose(position,
 // the substeps (pyb_setup.py:52-55,340-349).  The twist is constant while step_num < 25, so the pose after `moved`
 // env steps is closed form: translation moved*0.04*v, rotation by moved*0.04*|w| about w (Bullet composes one fixed
 // world-frame increment per substep).  vel = [v, w] as ReachDyn.velocity holds it.
-URGYM_HD void dyn_twist(const float *start, const float *end, float *vel, Quat &qs, float3 &axis, float &angle) {
+URGYM_HD void dyn_twist(const float *start, const float *end, float *vel, Quat &qs, float3 &axis, float &angle,
+                        float inv_duration = 0.5f) {
     qs = quat_from_euler(start[3], start[4], start[5]);
     Quat qe = quat_from_euler(end[3], end[4], end[5]);
     // getDifferenceQuaternion(start, end) = nearest(end) * start^-1                  pyb_setup.py:351-359
@@ -116,8 +121,8 @@ URGYM_HD void dyn_twist(const float *start, const float *end, float *vel, Quat &
     angle = 2.0f * atan2_fast(vn, w);                             // = 2 acos(w)
     if (s2 < 10.0f * 1.1920929e-7f || vn == 0.0f) axis = f3(1.0f, 0.0f, 0.0f);
     else axis = (1.0f / vn) * f3(d.x, d.y, d.z);
-    vel[0] = (end[0] - start[0]) * 0.5f; vel[1] = (end[1] - start[1]) * 0.5f; vel[2] = (end[2] - start[2]) * 0.5f;
-    vel[3] = axis.x * angle * 0.5f; vel[4] = axis.y * angle * 0.5f; vel[5] = axis.z * angle * 0.5f;
+    vel[0] = (end[0] - start[0]) * inv_duration; vel[1] = (end[1] - start[1]) * inv_duration; vel[2] = (end[2] - start[2]) * inv_duration;
+    vel[3] = axis.x * angle * inv_duration; vel[4] = axis.y * angle * inv_duration; vel[5] = axis.z * angle * inv_duration;
 }
 // episode cache: everything the step needs that depends on the episode constants E only (see Traits)
 template <int TASK> URGYM_HD void derive_cache(const float *E, float *C) {
@@ -129,10 +134,37 @@ template <int TASK> URGYM_HD void derive_cache(const float *E, float *C) {
     if (TASK == TASK_OBS) {
         ObstW O = obstacle_static(&E[3]);
         C[0] = O.u.x; C[1] = O.u.y; C[2] = O.u.z;
-    } else if (TASK == TASK_STA) {      // static obstacle: axis and the pose read-back of get_obs   reach.py:455-457
-        ObstW O = obstacle_static(&E[6]);
-        float3 e = euler_from_quat(O.q);
-        C[4] = O.u.x; C[5] = O.u.y; C[6] = O.u.z; C[7] = e.x; C[8] = e.y; C[9] = e.z;
+    } else if (TASK == TASK_STA) {
+        // ReachSta.set_velocity runs when obstacle_end is not all zero (core.py:307-308).  While the obstacle is farther
+        // than 0.05 m from obstacle_end[:3] it moves with the twist (end - start) / 1 s (reach.py:518-541); the test is
+        // made before every step, so the number of moving steps m follows from the episode constants alone.
+        bool armed = false;
+#pragma unroll
+        for (int k = 0; k < 6; k++) armed = armed || (E[12 + k] != 0.0f);
+        int m = 0;
+        float tw[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        Quat qs; qs.x = qs.y = qs.z = 0.0f; qs.w = 1.0f;
+        if (armed) {
+            float3 axis; float angle;
+            dyn_twist(&E[18], &E[12], tw, qs, axis, angle, 1.0f);       // twist from obstacle_START to obstacle_end
+            m = URGYM_MAX_STEPS;
+            for (int k = 0; k < URGYM_MAX_STEPS; k++) {
+                const float t = (float)k * URGYM_DT_ENV;
+                const float dx = E[12] - fmaf(t, tw[0], E[6]), dy = E[13] - fmaf(t, tw[1], E[7]), dz = E[14] - fmaf(t, tw[2], E[8]);
+                if (!(sqrtf(dx * dx + dy * dy + dz * dz) > 0.05f)) { m = k; break; }
+            }
+        }
+        C[4] = (float)m;
+        ObstW O = obstacle_static(&E[6]);       // orientation of the obstacle as placed (its own Euler triple)
+        if (m == 0) {                           // at rest: axis and the pose read-back of get_obs   reach.py:455-457
+            float3 e = euler_from_quat(O.q);
+            C[5] = O.u.x; C[6] = O.u.y; C[7] = O.u.z; C[8] = e.x; C[9] = e.y; C[10] = e.z;
+            C[11] = C[12] = C[13] = C[14] = 0.0f;
+        } else {
+            C[5] = O.q.x; C[6] = O.q.y; C[7] = O.q.z; C[8] = O.q.w;
+#pragma unroll
+            for (int k = 0; k < 6; k++) C[9 + k] = tw[k];
+        }
     } else if (TASK == TASK_DYN) {      // ReachDyn.set_velocity's twist is the same at every step of an episode
         Quat qs; float3 axis; float angle; float tw[6];
         dyn_twist(&E[6], &E[12], tw, qs, axis, angle);
@@ -144,16 +176,43 @@ template <int TASK> URGYM_HD void derive_cache(const float *E, float *C) {
 // obstacle pose after `moved` env steps of motion and its Euler read-back (get_base_rotation), from E[0..EH) and C.
 // Dyn: translation moved*0.04*v, rotation by moved*0.04*|w| about w = axis*angle/2 (Bullet composes one fixed
 // world-frame increment per substep), so the half angle is 0.5*t*|w| and sin(half)*axis = w * sin(half)/|w|.
-template <int TASK> URGYM_HD ObstW obstacle_cached(const float *E, const float *C, int moved, float3 &euler) {
+// pose after `moved` env steps of motion with twist tw = [v, w] from the pose (p0, qs)
+URGYM_HD void twist_pose(const float *p0, Quat qs, const float *tw, int moved, ObstW &O, float3 &euler) {
+    const float t = (float)moved * URGYM_DT_ENV;
+    O.c = f3(fmaf(t, tw[0], p0[0]), fmaf(t, tw[1], p0[1]), fmaf(t, tw[2], p0[2]));
+    const float3 w = f3(tw[3], tw[4], tw[5]);
+    const float wn2 = dot(w, w);
+    const float inv = wn2 > 0.0f ? rsqrt_f(wn2) : 0.0f;
+    float sn, cs;
+    sincos_fast(0.5f * t * (wn2 * inv), &sn, &cs);
+    const float k = sn * inv;
+    Quat r; r.x = w.x * k; r.y = w.y * k; r.z = w.z * k; r.w = cs;
+    O.q = quat_mul(r, qs);                              // world-frame increment on the left
+    O.u = quat_axis_z(O.q);
+    euler = euler_from_quat(O.q);
+}
+// ReachSta with a moving obstacle (injection-only path): rare, kept out of the hot instruction stream
+static URGYM_OOL void sta_moving_pose(const float *E, const float *C, int steps, ObstW &O, float3 &euler) {
+    const int m = (int)C[4];
+    Quat qs; qs.x = C[5]; qs.y = C[6]; qs.z = C[7]; qs.w = C[8];
+    twist_pose(&E[6], qs, &C[9], steps < m ? steps : m, O, euler);
+}
+// `steps`: env steps of the episode the obstacle has been through (capped inside: Dyn moves for 25, reach.py:735)
+template <int TASK> URGYM_HD ObstW obstacle_cached(const float *E, const float *C, int steps, float3 &euler) {
     ObstW O = obstacle_none();
     euler = f3(0, 0, 0);
     if (TASK == TASK_OBS) {
         O.c = f3(E[3], E[4], E[5]); O.u = f3(C[0], C[1], C[2]);
         euler = f3(E[6], E[7], E[8]);                   // Obs shows the Euler triple as sampled (quirk Q3)
     } else if (TASK == TASK_STA) {
-        O.c = f3(E[6], E[7], E[8]); O.u = f3(C[4], C[5], C[6]);
-        euler = f3(C[7], C[8], C[9]);
+        if (C[4] == 0.0f) {
+            O.c = f3(E[6], E[7], E[8]); O.u = f3(C[5], C[6], C[7]);
+            euler = f3(C[8], C[9], C[10]);
+        } else {
+            sta_moving_pose(E, C, steps, O, euler);
+        }
     } else if (TASK == TASK_DYN) {
+        const int moved = steps < 25 ? steps : 25;
         const float t = (float)moved * URGYM_DT_ENV;
         O.c = f3(fmaf(t, C[8], E[6]), fmaf(t, C[9], E[7]), fmaf(t, C[10], E[8]));
         const float3 w = f3(C[11], C[12], C[13]);
@@ -572,7 +631,7 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
     // 2. task.set_velocity + sim.step: obstacle pose after this step (twist from the episode cache)   core.py:305-309
     float3 oe;
     float vel[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    const ObstW O = obstacle_cached<TASK>(s.E, s.C, s.elapsed + 1 < 25 ? s.elapsed + 1 : 25, oe);
+    const ObstW O = obstacle_cached<TASK>(s.E, s.C, s.elapsed + 1, oe);
     if (TT::DYN) {
         if (s.elapsed < 25) {           // ReachDyn.velocity: the twist while step_num < 25, zeros afterwards
 #pragma unroll
@@ -640,7 +699,7 @@ URGYM_HD void env_observe(const ModelConst &M, const EnvState &s, const float *s
     typedef Traits<TASK> TT;
     float3 oe;
     float vel[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    const ObstW O = obstacle_cached<TASK>(s.E, s.C, s.elapsed < 25 ? s.elapsed : 25, oe);
+    const ObstW O = obstacle_cached<TASK>(s.E, s.C, s.elapsed, oe);
     if (TT::DYN) {
 #pragma unroll
         for (int k = 0; k < 6; k++) vel[k] = s.elapsed == 0 ? stale_vel[k] : (s.elapsed <= 25 ? s.C[8 + k] : 0.0f);
@@ -658,7 +717,7 @@ template <int TASK, int GEOM>
 URGYM_HD bool env_refresh(const ModelConst &M, EnvState &s, const float4 *hv, float *scratch, int cs) {
     typedef Traits<TASK> TT;
     float3 oe;
-    const ObstW O = obstacle_cached<TASK>(s.E, s.C, s.elapsed < 25 ? s.elapsed : 25, oe);
+    const ObstW O = obstacle_cached<TASK>(s.E, s.C, s.elapsed, oe);
     float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     bool coll = robot_pass<TASK, GEOM>(M, s.q, s.q, O, hv, true, ee, dist, scratch, cs);
     if (TT::HAS_OBST) {
@@ -755,7 +814,8 @@ URGYM_HD int sample_episode(const ModelConst &M, ResetStream rs, float *E, int k
 
 // RobotTaskEnv.reset (core.py:263-273): neutral pose, new episode constants, link_dist = last_dist at the reset
 // pose, first observation.  The velocity columns of `row` are left untouched (quirk Q4: the caller puts the
-// previous ReachDyn.velocity there).  Returns the rejection iterations used.
+// previous ReachDyn.velocity there).  ReachSta: s.E[12..24) (obstacle_end / obstacle_start) must hold the env's current
+// values on entry, the reset keeps them (reach.py:465-481).  Returns the rejection iterations used.
 template <int TASK, int GEOM>
 URGYM_HD int env_reset(const ModelConst &M, EnvState &s, ResetStream rs, const float4 *hv, float *row, int k_start = 0) {
     typedef Traits<TASK> TT;

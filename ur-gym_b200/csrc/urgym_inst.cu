@@ -26,8 +26,8 @@ cudaError_t NAME(urgym_inst_prepare_, URGYM_INST_TASK, URGYM_INST_GEOM)(const Mo
 // then compiled with the same floating-point flags (Makefile: FASTMATH for the capsule geometry), so the episode cache
 // rebuilt after a state injection is bit-identical to the one the handle's reset kernels write
 cudaError_t NAME(urgym_inst_observe_, URGYM_INST_TASK, URGYM_INST_GEOM)(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
-    return launch_observe<URGYM_INST_TASK>(M, A, s);
+    return launch_observe<URGYM_INST_TASK, URGYM_INST_GEOM>(M, A, s);
 }
 cudaError_t NAME(urgym_inst_derive_, URGYM_INST_TASK, URGYM_INST_GEOM)(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
-    return launch_derive<URGYM_INST_TASK>(M, A, s);
+    return launch_derive<URGYM_INST_TASK, URGYM_INST_GEOM>(M, A, s);
 }

@@ -193,7 +193,11 @@ __global__ void __launch_bounds__(URGYM_BLOCK, URGYM_STEP_MINBLOCKS) urgym_step_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (blockIdx.x == 0 && tid == 0) {                          // this launch is reset event number event[chain] + 1
         if (A.bump == 1) A.event[A.chain] += 1u;
-        if (A.bump == 2) for (int c = 0; c < URGYM_MAX_CHAINS; c++) A.event[c] += 1u;
+        if (A.bump == 2) {      // a whole step: one logical event for all chains (lagging chain counters catch up)
+            uint32_t m = 0u;
+            for (int c = 0; c < URGYM_MAX_CHAINS; c++) m = A.event[c] > m ? A.event[c] : m;
+            for (int c = 0; c < URGYM_MAX_CHAINS; c++) A.event[c] = m + 1u;
+        }
     }
     const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
     if (GEOM == GEOM_HULL) __syncthreads();
@@ -396,6 +400,7 @@ __device__ __forceinline__ unsigned long long reset_listed(const ModelConst &c_m
 #pragma unroll
                 for (int k = 0; k < 6; k++) row[24 + k] = vel[k];
             }
+            if (TASK == TASK_STA) load_E<TASK>(A.st, i, s.E);      // obstacle_end / obstacle_start survive a reset (reach.py:465-481)
             ResetStream rs;
             rs.key = A.key; rs.episode = event; rs.env_lo = (uint32_t)genv; rs.env_hi = (uint32_t)(genv >> 32);
             rs.bpi = TT::BPI; rs.iter = 0;
@@ -545,7 +550,14 @@ template <int TASK, int GEOM> constexpr size_t reset_smem_bytes() {
            (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
 
-static __global__ void urgym_bump_kernel(uint32_t *event) { for (int c = 0; c < URGYM_MAX_CHAINS; c++) event[c] += 1u; }
+// every chain's reset-event counter := max over the chains + add.  add = 1: a reset event of its own (explicit reset,
+// host-buffer step); add = 0: equalise the counters (first node of a chained step graph), so that chains stepped unequally
+// before can never draw from a (seed, env, event) position that another layout of the chains has already used.
+static __global__ void urgym_bump_kernel(uint32_t *event, uint32_t add) {
+    uint32_t m = 0u;
+    for (int c = 0; c < URGYM_MAX_CHAINS; c++) m = event[c] > m ? event[c] : m;
+    for (int c = 0; c < URGYM_MAX_CHAINS; c++) event[c] = m + add;
+}
 
 template <int TASK> __device__ __forceinline__ void write_rows(const AuxArgs &A, int64_t i, const float *row) {
     constexpr int D = Traits<TASK>::OBS, G = Traits<TASK>::GOAL;
@@ -554,7 +566,9 @@ template <int TASK> __device__ __forceinline__ void write_rows(const AuxArgs &A,
     if (A.des) for (int k = 0; k < G; k++) A.des[i * G + k] = row[12 + k];
 }
 
-template <int TASK>
+// (GEOM is a template parameter of the task-only kernels too: each (task, geometry) translation unit is compiled with its
+// own floating-point flags, and a kernel shared between them would be one COMDAT copy built with whichever flags won)
+template <int TASK, int GEOM>
 __global__ void __launch_bounds__(URGYM_BLOCK) urgym_observe_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
     typedef Traits<TASK> TT;
     const int64_t i = (int64_t)blockIdx.x * URGYM_BLOCK + threadIdx.x;
@@ -572,7 +586,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_observe_kernel(const __grid
 }
 
 // rebuild the hot planes from the episode constants E (after urgym_set_state wrote a goal / obstacle field)
-template <int TASK>
+template <int TASK, int GEOM>
 __global__ void __launch_bounds__(URGYM_BLOCK) urgym_derive_kernel(const AuxArgs A) {
     const int64_t i = (int64_t)blockIdx.x * URGYM_BLOCK + threadIdx.x;
     if (i >= A.n) return;
@@ -645,13 +659,13 @@ template <int TASK, int GEOM> cudaError_t prepare_kernels(const ModelConst &, co
     return e;
 }
 
-template <int TASK> cudaError_t launch_observe(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
-    urgym_observe_kernel<TASK><<<grid_for(A.n), URGYM_BLOCK, 0, s>>>(M, A);
+template <int TASK, int GEOM> cudaError_t launch_observe(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
+    urgym_observe_kernel<TASK, GEOM><<<grid_for(A.n), URGYM_BLOCK, 0, s>>>(M, A);
     return cudaGetLastError();
 }
 
-template <int TASK> cudaError_t launch_derive(const ModelConst &, const AuxArgs &A, cudaStream_t s) {
-    urgym_derive_kernel<TASK><<<grid_for(A.n), URGYM_BLOCK, 0, s>>>(A);
+template <int TASK, int GEOM> cudaError_t launch_derive(const ModelConst &, const AuxArgs &A, cudaStream_t s) {
+    urgym_derive_kernel<TASK, GEOM><<<grid_for(A.n), URGYM_BLOCK, 0, s>>>(A);
     return cudaGetLastError();
 }
 

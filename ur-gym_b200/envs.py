@@ -108,7 +108,9 @@ class Task:
     def obstacle(self) -> np.ndarray:
         return self._env.vec.get_state("obstacle")[0].cpu().numpy().astype(np.float64)
 
-    obstacle_start = obstacle
+    @property
+    def obstacle_start(self) -> np.ndarray:
+        return self._env.vec.get_state("obstacle_start")[0].cpu().numpy().astype(np.float64)
 
     @property
     def obstacle_end(self) -> np.ndarray:
@@ -133,10 +135,14 @@ class Task:
             if t.size != 18:
                 raise ValueError("expected goal(6) + obstacle_start(6) + obstacle_end(6)")
             v.set_state("goal", t[None, :6]); v.set_state("obstacle", t[None, 6:12]); v.set_state("obstacle_end", t[None, 12:])
+        elif self._env.spec.id == "UR5StaReach-v1" and t.size == 18:
+            # moving obstacle: obstacle = obstacle_start = t[6:12], obstacle_end = t[12:]   reach.py:491-499
+            v.set_state("goal", t[None, :6]); v.set_state("obstacle", t[None, 6:12])
+            v.set_state("obstacle_start", t[None, 6:12]); v.set_state("obstacle_end", t[None, 12:])
         else:
             if t.size != G + 6:
-                raise NotImplementedError("moving-obstacle injection for ReachSta (18 values) is not supported yet")
-            v.set_state("goal", t[None, :G]); v.set_state("obstacle", t[None, G:])
+                raise ValueError(f"expected {G + 6} values (goal + obstacle)" + (" or 18" if G == 6 else ""))
+            v.set_state("goal", t[None, :G]); v.set_state("obstacle", t[None, G:])     # (Sta: start / end stay as they are)
         self.collision = bool(v.refresh()[0].item())
 
     # -- pure functions of arrays (utils.py formulas)

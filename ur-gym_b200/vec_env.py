@@ -41,6 +41,7 @@ class UR5VecEnv:
         self.env_id, self.task = env_id, nat.TASK_IDS[env_id]
         self.num_envs, self.device_index, self.seed, self.offset = int(num_envs), int(device), int(seed), int(env_index_offset)
         self.device = torch.device("cuda", self.device_index)
+        self.geometry = geometry
         self.L = nat.lib()
         self.obs_dim, self.goal_dim = self.L.urgym_obs_dim(self.task), self.L.urgym_goal_dim(self.task)
         h = ctypes.c_void_p()
@@ -69,6 +70,9 @@ class UR5VecEnv:
                            _ptr(self.truncated), _ptr(self.is_success), _ptr(self.terminal_obs), _ptr(self.terminal_achieved)]
         self._obs = self._obs_dict(self.obs)
         self._info = {"is_success": self.is_success, "terminal_observation": self.terminal_obs}
+        # RobotTaskEnv.__init__ ends with reset() (core.py:237); a batch constructor that drew 1 Mi episodes nobody asked
+        # for would be wasteful, so the first reset stays explicit -- but nothing may run on the zero-filled pool
+        self._initialised = False
 
     # ---- plumbing
     def _stream(self):
@@ -94,8 +98,16 @@ class UR5VecEnv:
         """reset all envs (mask None) or those with a non-zero mask byte; returns the observation dict"""
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        if mask is None:
+            self._initialised = True
+        self._need_reset()
         nat.check(self.h, self.L.urgym_reset(self.h, _ptr(mask), _ptr(self.obs), _ptr(self.achieved), None, self._stream()))
         return self._obs
+
+    def _need_reset(self):
+        if not self._initialised:
+            raise nat.UrgymError("reset() (all envs) or load_state_dict() must be called before step / observe / "
+                                 "reset(mask): the state pool is zero-filled (q = 0, no goal)")
 
     def step(self, actions: torch.Tensor):
         """actions float32 [N,6] on the device.  Returns (obs dict, reward, terminated, truncated, info); for envs that
@@ -106,6 +118,8 @@ class UR5VecEnv:
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
         if actions.shape != (self.num_envs, 6):
             raise ValueError(f"actions must have shape ({self.num_envs}, 6)")
+        if not self._initialised:
+            self._need_reset()
         rc = self.L.urgym_step(self.h, actions.data_ptr(), *self._step_ptrs,
                                torch.cuda.current_stream(self.device).cuda_stream)
         if rc != 0:
@@ -124,6 +138,7 @@ class UR5VecEnv:
         chains > 1 splits the envs into that many contiguous ranges, each advanced by its own branch of the graph
         (urgym_step_range): the branches are independent, so one range's auto-reset kernel overlaps another range's
         step kernel.  Results are identical to chains = 1."""
+        self._need_reset()
         for a in action_buffers:
             if a.device != self.device or a.dtype != torch.float32 or not a.is_contiguous() or a.shape != (self.num_envs, 6):
                 raise ValueError("capture_steps needs contiguous float32 [N,6] tensors on the simulator's device")
@@ -140,6 +155,8 @@ class UR5VecEnv:
                 for a in action_buffers:
                     self.step(a)
             else:
+                # chains count their own reset events: start from a common position whatever was stepped before
+                nat.check(self.h, self.L.urgym_sync_events(self.h, main.cuda_stream))
                 side = [torch.cuda.Stream(self.device) for _ in ranges[1:]]
                 fork = torch.cuda.Event()
                 fork.record(main)
@@ -163,6 +180,7 @@ class UR5VecEnv:
         nat.check(self.h, self.L.urgym_set_seed(self.h, ctypes.c_uint64(self.seed & (2 ** 64 - 1))))
 
     def observe(self) -> Dict[str, torch.Tensor]:
+        self._need_reset()
         with torch.cuda.device(self.device):
             nat.check(self.h, self.L.urgym_observe(self.h, _ptr(self.obs), None, None, self._stream()))
         return self._obs_dict(self.obs)
@@ -170,6 +188,7 @@ class UR5VecEnv:
     # ---- state access: injection hooks of the reference + checkpointing
     _FIELDS = {"q": (nat.F_Q, 6, torch.float32), "goal": (nat.F_GOAL, None, torch.float32),
                "obstacle": (nat.F_OBSTACLE, 6, torch.float32), "obstacle_end": (nat.F_OBSTACLE_END, 6, torch.float32),
+               "obstacle_start": (nat.F_OBSTACLE_START, 6, torch.float32),
                "link_dist": (nat.F_LINK_DIST, 5, torch.float32), "elapsed": (nat.F_ELAPSED, 0, torch.int32),
                "ep_return": (nat.F_EP_RETURN, 0, torch.float32), "velocity": (nat.F_VELOCITY, 6, torch.float32),
                "hot": (nat.F_HOT, 24, torch.float32)}
@@ -203,26 +222,47 @@ class UR5VecEnv:
             nat.check(self.h, self.L.urgym_refresh(self.h, _ptr(coll), self._stream()))
         return coll
 
-    def state_dict(self) -> Dict[str, object]:
-        names = ["q", "goal", "elapsed", "ep_return"]
+    def _state_names(self):
+        # restore order: episode constants first (setting one re-derives the hot planes), then the per-step state, then
+        # the raw hot words -- restored last they make a restore bit-exact whatever the dict's own order is
+        names = ["goal"]
         if self.task != 0:
-            names += ["obstacle", "link_dist"]
+            names += ["obstacle"]
+        if self.task in (2, 3):
+            names += ["obstacle_end", "obstacle_start"] if self.task == 2 else ["obstacle_end"]
+        names += ["q", "elapsed", "ep_return"]
+        if self.task != 0:
+            names += ["link_dist"]
         if self.task == 3:
-            names += ["obstacle_end", "velocity"]
+            names += ["velocity"]
+        return names + ["hot"]
+
+    def state_dict(self) -> Dict[str, object]:
         ev = ctypes.c_uint32()
         nat.check(self.h, self.L.urgym_get_event(self.h, ctypes.byref(ev)))
-        # "hot" (the step kernel's episode cache) last: it is re-derived whenever a goal / obstacle field is set, and the
-        # raw words restored afterwards make the restore bit-exact
-        d = {k: self.get_state(k) for k in names + ["hot"]}
+        d = {k: self.get_state(k) for k in self._state_names()}
         d["event"] = int(ev.value)
+        d["meta"] = {"env_id": self.env_id, "num_envs": self.num_envs, "seed": self.seed, "env_index_offset": self.offset,
+                     "geometry": self.geometry, "link_dist": self.link_dist_mode}
         return d
 
-    def load_state_dict(self, d: Dict[str, object]) -> None:
-        for k, v in d.items():
-            if k == "event":
-                nat.check(self.h, self.L.urgym_set_event(self.h, int(v)))
-            else:
-                self.set_state(k, v)
+    def load_state_dict(self, d: Dict[str, object], strict: bool = True) -> None:
+        """restore a state_dict().  strict: the dict must come from a simulator with the same task, size, seed, env index
+        offset, geometry and link-distance mode (the reset stream is keyed by seed and global env index: restoring into
+        another configuration would silently continue with different episodes)."""
+        meta = d.get("meta")
+        if strict:
+            mine = {"env_id": self.env_id, "num_envs": self.num_envs, "seed": self.seed, "env_index_offset": self.offset,
+                    "geometry": self.geometry, "link_dist": self.link_dist_mode}
+            if meta != mine:
+                raise nat.UrgymError(f"state_dict was taken from {meta}, this simulator is {mine}")
+        missing = [k for k in self._state_names() + ["event"] if k not in d]
+        if missing:
+            raise nat.UrgymError(f"state_dict lacks {missing}")
+        for k in self._state_names():
+            self.set_state(k, d[k])
+        nat.check(self.h, self.L.urgym_set_event(self.h, int(d["event"])))
+        self._initialised = True
 
     def stats(self, reset: bool = True) -> Dict[str, float]:
         """per-shard episode statistics accumulated on the device since the last reset=True call"""
@@ -239,6 +279,7 @@ class UR5VecEnv:
     def step_host(self, actions, out: Dict[str, torch.Tensor]):
         """actions and the tensors in `out` (keys obs, reward, terminated, truncated, is_success and optionally
         terminal_obs) are HOST tensors, ideally pinned; copies in, steps, copies out, synchronises."""
+        self._need_reset()
         nat.check(self.h, self.L.urgym_step_host(self.h, _ptr(actions), _ptr(out["obs"]), None, None, _ptr(out["reward"]),
                                                  _ptr(out["terminated"]), _ptr(out["truncated"]), _ptr(out["is_success"]),
                                                  _ptr(out.get("terminal_obs")), None))
