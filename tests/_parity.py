@@ -29,6 +29,12 @@ def _rotation_angle(e1, e2):
 
 GIMBAL_ZONE = np.deg2rad(10.0)
 gimbal_fallbacks = [0]
+# getEulerFromQuaternion switches to its gimbal branch (roll := 0, pitch := +-pi/2 exactly) at |sarg| >= 0.99999, i.e.
+# within acos(0.99999) = 4.47e-3 rad of the pole: a threshold of the reference's own algorithm.  When sarg lies within
+# 1e-6 of it, FP32 and FP64 may take different branches; the branch's triple (pitch snapped to the pole, yaw from
+# 2 atan2) then differs from the regular one by a rotation of up to about twice that angle.
+GIMBAL_BRANCH_ANGLE = float(np.arccos(0.99999 - 2e-6))
+gimbal_branch_exempt = [0]
 
 
 LD_COLS = {"UR5OriReach-v1": [], "UR5ObsReach-v1": list(range(21, 26)), "UR5StaReach-v1": list(range(24, 29)),
@@ -60,6 +66,11 @@ def obs_close(env_id, got, want, ld_tol=None):
         if a > ANG_TOL and abs(abs(w[1]) - np.pi / 2) < GIMBAL_ZONE and c != 3:    # goal triples (c == 3) are copied, never recomputed
             a = _rotation_angle(g, w)
             gimbal_fallbacks[0] += 1
+            on_pole = [abs(abs(x[1]) - np.pi / 2) < 1e-6 and x[0] == 0.0 for x in (g, w)]
+            if a > ANG_TOL and on_pole[0] != on_pole[1] and a <= 2.0 * GIMBAL_BRANCH_ANGLE and \
+                    abs(abs(g[1]) - np.pi / 2) <= GIMBAL_BRANCH_ANGLE and abs(abs(w[1]) - np.pi / 2) <= GIMBAL_BRANCH_ANGLE:
+                gimbal_branch_exempt[0] += 1        # exactly one side took the gimbal branch, right at its threshold
+                a = 0.0
         ang = max(ang, a)
     return lin, ang
 

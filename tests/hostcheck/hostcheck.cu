@@ -14,6 +14,7 @@
 using namespace urgym;
 
 static ModelConst g_M;
+static int g_ld_mode = 0;      // link-distance mode: selects the GEOM | GEOM_WB instantiations
 static std::vector<float4> g_hull;
 static bool g_init = false;
 static void init() {
@@ -104,7 +105,10 @@ static void observe_t(int64_t n, HcState S, const float *stale_vel, float *obs) 
 #define SWITCH(fn, ...)                                                                                       \
     do {                                                                                                      \
         if (geom != HC_GEOM) return -1;                                                                       \
-        if (task == 0) fn<0, HC_GEOM>(__VA_ARGS__); else if (task == 1) fn<1, HC_GEOM>(__VA_ARGS__);          \
+        if (g_ld_mode && task != 0) {                                                                         \
+            if (task == 1) fn<1, HC_GEOM | GEOM_WB>(__VA_ARGS__);                                             \
+            else if (task == 2) fn<2, HC_GEOM | GEOM_WB>(__VA_ARGS__); else fn<3, HC_GEOM | GEOM_WB>(__VA_ARGS__); \
+        } else if (task == 0) fn<0, HC_GEOM>(__VA_ARGS__); else if (task == 1) fn<1, HC_GEOM>(__VA_ARGS__);   \
         else if (task == 2) fn<2, HC_GEOM>(__VA_ARGS__); else fn<3, HC_GEOM>(__VA_ARGS__);                    \
     } while (0)
 
@@ -156,7 +160,13 @@ void hc_set_obstacle(float r, float h, float margin) {
     init();
     g_M.obst_r = r; g_M.obst_h = h; g_M.obst_margin = margin;
 }
-void hc_set_ld_mode(int mode) { init(); g_M.ld_mode = mode; }
+void hc_set_ld_mode(int mode) { g_ld_mode = mode; }
+#ifdef URGYM_HC_COUNTERS
+void hc_counters(unsigned long long *out) {     // 10 slow, 10 slow hits, 10 probe hits, 10 aabb rejects, 9 need
+    for (int k = 0; k < 10; k++) { out[k] = g_hc_slow[k]; out[10 + k] = g_hc_slow_hit[k]; out[20 + k] = g_hc_probe_hit[k]; out[30 + k] = g_hc_aabb_rej[k]; }
+    for (int k = 0; k < 9; k++) out[40 + k] = g_hc_need[k];
+}
+#endif
 void hc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
     uint4 r = philox4x32_10(make_uint4(c[0], c[1], c[2], c[3]), make_uint2(k[0], k[1]));
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_field_kernel(const FieldArg
 
 // ------------------------------------------------------------------------------------------------ host side
 struct urgym_env {
-    int task, geom, device;
+    int task, geom, device;     // geom: GEOM template value = geometry | link-distance mode << 1
     int64_t n, offset;
     uint64_t seed;
     uint32_t *d_event;      // device-resident reset-event counter: position of the counter-based reset stream.
@@ -129,29 +129,43 @@ extern "C" int64_t urgym_launch_count(const urgym_env_t *h) { return h ? h->laun
 
 static inline uint2 key_of(uint64_t seed) { return make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)); }
 
-// [geom][task]
-static const step_launcher_t k_step[2][4] = {
+// [geom | ld_mode << 1][task]  (GEOM template value: bit 0 geometry, bit 1 link-distance mode "workbench")
+static const step_launcher_t k_step[4][4] = {
     {urgym_inst_step_0_0, urgym_inst_step_1_0, urgym_inst_step_2_0, urgym_inst_step_3_0},
-    {urgym_inst_step_0_1, urgym_inst_step_1_1, urgym_inst_step_2_1, urgym_inst_step_3_1}};
-static const aux_launcher_t k_reset[2][4] = {
+    {urgym_inst_step_0_1, urgym_inst_step_1_1, urgym_inst_step_2_1, urgym_inst_step_3_1},
+    {nullptr, urgym_inst_step_1_2, urgym_inst_step_2_2, urgym_inst_step_3_2},
+    {nullptr, urgym_inst_step_1_3, urgym_inst_step_2_3, urgym_inst_step_3_3}};
+static const aux_launcher_t k_reset[4][4] = {
     {urgym_inst_reset_0_0, urgym_inst_reset_1_0, urgym_inst_reset_2_0, urgym_inst_reset_3_0},
-    {urgym_inst_reset_0_1, urgym_inst_reset_1_1, urgym_inst_reset_2_1, urgym_inst_reset_3_1}};
-static const aux_launcher_t k_autoreset[2][4] = {
+    {urgym_inst_reset_0_1, urgym_inst_reset_1_1, urgym_inst_reset_2_1, urgym_inst_reset_3_1},
+    {nullptr, urgym_inst_reset_1_2, urgym_inst_reset_2_2, urgym_inst_reset_3_2},
+    {nullptr, urgym_inst_reset_1_3, urgym_inst_reset_2_3, urgym_inst_reset_3_3}};
+static const aux_launcher_t k_autoreset[4][4] = {
     {urgym_inst_autoreset_0_0, urgym_inst_autoreset_1_0, urgym_inst_autoreset_2_0, urgym_inst_autoreset_3_0},
-    {urgym_inst_autoreset_0_1, urgym_inst_autoreset_1_1, urgym_inst_autoreset_2_1, urgym_inst_autoreset_3_1}};
-static const aux_launcher_t k_refresh[2][4] = {
+    {urgym_inst_autoreset_0_1, urgym_inst_autoreset_1_1, urgym_inst_autoreset_2_1, urgym_inst_autoreset_3_1},
+    {nullptr, urgym_inst_autoreset_1_2, urgym_inst_autoreset_2_2, urgym_inst_autoreset_3_2},
+    {nullptr, urgym_inst_autoreset_1_3, urgym_inst_autoreset_2_3, urgym_inst_autoreset_3_3}};
+static const aux_launcher_t k_refresh[4][4] = {
     {urgym_inst_refresh_0_0, urgym_inst_refresh_1_0, urgym_inst_refresh_2_0, urgym_inst_refresh_3_0},
-    {urgym_inst_refresh_0_1, urgym_inst_refresh_1_1, urgym_inst_refresh_2_1, urgym_inst_refresh_3_1}};
-static const aux_launcher_t k_observe[2][4] = {
+    {urgym_inst_refresh_0_1, urgym_inst_refresh_1_1, urgym_inst_refresh_2_1, urgym_inst_refresh_3_1},
+    {nullptr, urgym_inst_refresh_1_2, urgym_inst_refresh_2_2, urgym_inst_refresh_3_2},
+    {nullptr, urgym_inst_refresh_1_3, urgym_inst_refresh_2_3, urgym_inst_refresh_3_3}};
+static const aux_launcher_t k_observe[4][4] = {
     {urgym_inst_observe_0_0, urgym_inst_observe_1_0, urgym_inst_observe_2_0, urgym_inst_observe_3_0},
-    {urgym_inst_observe_0_1, urgym_inst_observe_1_1, urgym_inst_observe_2_1, urgym_inst_observe_3_1}};
-static const aux_launcher_t k_derive[2][4] = {
+    {urgym_inst_observe_0_1, urgym_inst_observe_1_1, urgym_inst_observe_2_1, urgym_inst_observe_3_1},
+    {nullptr, urgym_inst_observe_1_2, urgym_inst_observe_2_2, urgym_inst_observe_3_2},
+    {nullptr, urgym_inst_observe_1_3, urgym_inst_observe_2_3, urgym_inst_observe_3_3}};
+static const aux_launcher_t k_derive[4][4] = {
     {urgym_inst_derive_0_0, urgym_inst_derive_1_0, urgym_inst_derive_2_0, urgym_inst_derive_3_0},
-    {urgym_inst_derive_0_1, urgym_inst_derive_1_1, urgym_inst_derive_2_1, urgym_inst_derive_3_1}};
+    {urgym_inst_derive_0_1, urgym_inst_derive_1_1, urgym_inst_derive_2_1, urgym_inst_derive_3_1},
+    {nullptr, urgym_inst_derive_1_2, urgym_inst_derive_2_2, urgym_inst_derive_3_2},
+    {nullptr, urgym_inst_derive_1_3, urgym_inst_derive_2_3, urgym_inst_derive_3_3}};
 
-static const aux_launcher_t k_prepare[2][4] = {
+static const aux_launcher_t k_prepare[4][4] = {
     {urgym_inst_prepare_0_0, urgym_inst_prepare_1_0, urgym_inst_prepare_2_0, urgym_inst_prepare_3_0},
-    {urgym_inst_prepare_0_1, urgym_inst_prepare_1_1, urgym_inst_prepare_2_1, urgym_inst_prepare_3_1}};
+    {urgym_inst_prepare_0_1, urgym_inst_prepare_1_1, urgym_inst_prepare_2_1, urgym_inst_prepare_3_1},
+    {nullptr, urgym_inst_prepare_1_2, urgym_inst_prepare_2_2, urgym_inst_prepare_3_2},
+    {nullptr, urgym_inst_prepare_1_3, urgym_inst_prepare_2_3, urgym_inst_prepare_3_3}};
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -205,7 +219,7 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
             memset(&dummy, 0, sizeof(dummy));
             if ((e = k_prepare[geom][task](h->model, dummy, 0)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
         }
-        if (geom == URGYM_GEOM_HULL) {
+        if ((geom & 1) == URGYM_GEOM_HULL) {
             static float4 hv[UR5E_NUM_HULL_VERTS];
             for (int i = 0; i < UR5E_NUM_HULL_VERTS; i++)
                 hv[i] = make_float4((float)UR5E_HULL_VERTS[3 * i], (float)UR5E_HULL_VERTS[3 * i + 1], (float)UR5E_HULL_VERTS[3 * i + 2], 0.0f);
@@ -267,7 +281,12 @@ extern "C" int urgym_set_link_dist_mode(urgym_env_t *h, int mode) {
     if (!h) return URGYM_EINVAL;
     if (mode != URGYM_LD_OBSTACLE && mode != URGYM_LD_WORKBENCH) return fail(h, URGYM_EINVAL, "urgym_set_link_dist_mode: unknown mode%s", "");
     if (h->task == 0) return fail(h, URGYM_EUNSUPPORTED, "urgym_set_link_dist_mode: UR5OriReach has no link_dist%s", "");
-    h->model.ld_mode = mode;        // the model constants travel with every launch (__grid_constant__)
+    const int geom = (h->geom & 1) | (mode << 1);
+    AuxArgs dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    CK(cudaSetDevice(h->device));
+    CK(k_prepare[geom][h->task](h->model, dummy, 0));       // the mode has its own kernel instantiations
+    h->geom = geom;
     return URGYM_OK;
 }
 extern "C" int urgym_set_seed(urgym_env_t *h, uint64_t seed) {

@@ -152,9 +152,6 @@ struct alignas(16) ModelConst {
     float neutral_ee[6];                           // EE position + PyBullet Euler triple
     float neutral_ca[7][3], neutral_cb[7][3];      // world capsule segments of links 0..6
     float neutral_R[7][9], neutral_p[7][3];        // world link poses (hull mode)
-    // what get_link_distances measures (urgym_b200.h URGYM_LD_*): 0 = links vs obstacle (pyb_setup.py:439-456 as shipped),
-    // 1 = per link the smallest of the distances to obstacle, table and track (the method's docstring)
-    int ld_mode;
 };
 
 #define URGYM_PI_F 3.14159265358979323846f

@@ -19,7 +19,11 @@
 namespace urgym {
 
 enum { TASK_ORI = 0, TASK_OBS = 1, TASK_STA = 2, TASK_DYN = 3 };
-enum { GEOM_HULL = 0, GEOM_CAPSULE = 1 };
+// GEOM template values: bit 0 = link geometry, bit 1 = link-distance mode "workbench" (urgym_b200.h URGYM_LD_WORKBENCH).
+// The mode is a compile-time property of its own kernel instantiations: the default kernels carry none of its code.
+enum { GEOM_HULL = 0, GEOM_CAPSULE = 1, GEOM_WB = 2 };
+#define URGYM_BASE(G) ((G) & 1)
+#define URGYM_WB(G) (((G) & GEOM_WB) != 0)
 
 #define URGYM_MAX_STEPS 100          /* UR_gym/__init__.py:22,28,34,41 */
 #define URGYM_MAX_RESET_ITERS 256    /* rejection loop bound; P(reached) ~ 0.83^256 */
@@ -379,7 +383,7 @@ template <> struct LinkShape<GEOM_HULL> {
 template <int TASK, int GEOM>
 URGYM_HD float target_obstacle_dist(const ModelConst &M, const float *goal, const ObstW &O) {
     float3 g = f3(goal[0], goal[1], goal[2]);
-    if (GEOM == GEOM_CAPSULE) {
+    if (URGYM_BASE(GEOM) == GEOM_CAPSULE) {
         float3 oa = O.c - M.fit_obst_h * O.u, ob = O.c + M.fit_obst_h * O.u;
         return sqrtf(point_seg_dist2(g, oa, ob)) - M.tgt_cap_m[TASK] - M.obst_cap_m;
     }
@@ -403,7 +407,7 @@ URGYM_HD bool robot_pass_rolled(const ModelConst &M, const float *qrow, const Ob
                          float *ee, float &d0, float &d1, float &d2, float &d3, float &d4) {
     Pose T;
     pose_identity(T);
-    LinkShape<GEOM> s1, s2, s3, cur;
+    LinkShape<URGYM_BASE(GEOM)> s1, s2, s3, cur;
     bool hit = false;
 #pragma unroll 1
     for (int l = 1; l < 7; l++) {
@@ -414,7 +418,7 @@ URGYM_HD bool robot_pass_rolled(const ModelConst &M, const float *qrow, const Ob
                 if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
                     float d = cur.obstacle_dist(M, l, O);
                     hit = hit || (d <= URGYM_COLLISION_MARGIN);
-                    if (M.ld_mode) d = fminf(d, fminf(cur.box_dist(M, l, 0), cur.box_dist(M, l, 1)));
+                    if (URGYM_WB(GEOM)) d = fminf(d, fminf(cur.box_dist(M, l, 0), cur.box_dist(M, l, 1)));
                     if (l == 2) d0 = d; else if (l == 3) d1 = d; else if (l == 4) d2 = d; else if (l == 5) d3 = d; else d4 = d;
                 }
 #pragma unroll 1
@@ -437,8 +441,11 @@ URGYM_HD bool robot_pass_rolled(const ModelConst &M, const float *qrow, const Ob
 // link pairs, so each distance routine exists once in the instruction stream.
 // scratch layout: 36 floats capsule endpoints (link 1..6: a.xyz b.xyz), 5 floats link-obstacle distances.
 #define URGYM_SCRATCH_FLOATS 41
+#ifdef URGYM_HC_COUNTERS
+static unsigned long long g_hc_slow[10], g_hc_slow_hit[10], g_hc_probe_hit[10], g_hc_aabb_rej[10], g_hc_need[9];
+#endif
 // link-distance mode "workbench": fold the link's distances to the table and the track into the link-obstacle
-// distances of the scratch column.  Out of line and behind a warp-uniform branch: the default mode pays two instructions.
+// distances of the scratch column
 static URGYM_OOL void workbench_link_dist(const ModelConst &M, float *cap, int cs) {
 #pragma unroll 1
     for (int l = 2; l < 7; l++) {
@@ -449,7 +456,7 @@ static URGYM_OOL void workbench_link_dist(const ModelConst &M, float *cap, int c
         d = fminf(d, fminf(L.box_dist(M, l, 0), L.box_dist(M, l, 1)));
     }
 }
-template <int TASK>
+template <int TASK, bool WORKBENCH>
 URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const ObstW &O, bool collide, float *ee,
                                  float *dist, float *cap, int cs) {
     PoseP T;
@@ -502,6 +509,9 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
     }
     while (slow) {          // exact segment-box distance for the few (link, box) cases left
         const int k = __ffs_hd(slow) - 1;
+#ifdef URGYM_HC_COUNTERS
+        g_hc_slow[k]++;
+#endif
         slow &= slow - 1u;
         const int l = 2 + (k >> 1), box = k & 1;
         const float *c = cap + (l - 1) * 6 * cs;
@@ -509,6 +519,16 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
         const float3 bc = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
         const float3 bh = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
         hit = hit || (sqrtf(seg_box_dist2(a, b, bc, bh)) - M.fit_box[l] - M.box_margin[box] <= URGYM_COLLISION_MARGIN);
+#ifdef URGYM_HC_COUNTERS
+        if (sqrtf(seg_box_dist2(a, b, bc, bh)) - M.fit_box[l] - M.box_margin[box] <= URGYM_COLLISION_MARGIN) g_hc_slow_hit[k]++;
+        {   // would a 3-point probe have decided it?
+            float reach = URGYM_COLLISION_MARGIN + M.fit_box[l] + M.box_margin[box];
+            float3 m = 0.5f * (a + b);
+            float pm = fminf(fminf(point_box_dist2(a, bc, bh), point_box_dist2(b, bc, bh)), point_box_dist2(m, bc, bh));
+            if (pm <= reach * reach) g_hc_probe_hit[k]++;
+            if (seg_box_lower2(a, b, bc, bh) > reach * reach) g_hc_aabb_rej[k]++;
+        }
+#endif
     }
     // self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6), pair index p = 0..8 in that order: a broad phase for all nine with static
     // indices, then the exact segment-segment test only for the pairs it leaves, in a rolled loop.
@@ -547,6 +567,9 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
         }
         while (need) {
             const int p = __ffs_hd(need) - 1;
+#ifdef URGYM_HC_COUNTERS
+            g_hc_need[p]++;
+#endif
             need &= need - 1u;
             const int l1 = p < 4 ? 1 : (p < 7 ? 2 : 3);
             const int l2 = p < 4 ? p + 3 : (p < 7 ? p : p - 2);
@@ -557,7 +580,7 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
         }
     }
     if (Traits<TASK>::HAS_OBST) {
-        if (M.ld_mode) workbench_link_dist(M, cap, cs);
+        if (WORKBENCH) workbench_link_dist(M, cap, cs);
 #pragma unroll
         for (int k = 0; k < 5; k++) dist[k] = cap[(36 + k) * cs];
     }
@@ -568,7 +591,7 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
 template <int TASK, int GEOM>
 URGYM_HD bool robot_pass(const ModelConst &M, const float *q, const float *qrow, const ObstW &O, const float4 *hv,
                          bool collide, float *ee, float *dist, float *scratch, int cs) {
-    if (GEOM == GEOM_CAPSULE) return robot_pass_capsule<TASK>(M, q, O, collide, ee, dist, scratch, cs);
+    if (URGYM_BASE(GEOM) == GEOM_CAPSULE) return robot_pass_capsule<TASK, URGYM_WB(GEOM)>(M, q, O, collide, ee, dist, scratch, cs);
     return robot_pass_rolled<TASK, GEOM>(M, qrow, O, hv, collide, ee, dist[0], dist[1], dist[2], dist[3], dist[4]);
 }
 
@@ -642,7 +665,7 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
     }
     // 3. FK and collision                                                                      core.py:310
     float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    if (GEOM != GEOM_CAPSULE) {
+    if (URGYM_BASE(GEOM) != GEOM_CAPSULE) {
 #pragma unroll
         for (int k = 0; k < 6; k++) row[6 + k] = s.q[k];
     }
@@ -830,10 +853,10 @@ URGYM_HD int env_reset(const ModelConst &M, EnvState &s, ResetStream rs, const f
     if (TT::HAS_OBST) {
 #pragma unroll 1
         for (int l = 2; l < 7; l++) {                   // reach.py:323-324,478-479,680-681
-            LinkShape<GEOM> L;
+            LinkShape<URGYM_BASE(GEOM)> L;
             L.set_neutral(M, l, hv);
             float d = L.obstacle_dist(M, l, O);
-            if (M.ld_mode) d = fminf(d, fminf(L.box_dist(M, l, 0), L.box_dist(M, l, 1)));
+            if (URGYM_WB(GEOM)) d = fminf(d, fminf(L.box_dist(M, l, 0), L.box_dist(M, l, 1)));
             if (l == 2) s.ld[0] = d; else if (l == 3) s.ld[1] = d; else if (l == 4) s.ld[2] = d; else if (l == 5) s.ld[3] = d; else s.ld[4] = d;
         }
     } else {

@@ -162,7 +162,7 @@ __device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_c
 // stage the hull vertices in shared memory (hull mode only): every lane of a warp walks the same vertex list, so
 // the support-function loop reads shared memory as a broadcast
 template <int GEOM> __device__ __forceinline__ const float4 *stage_hull(const float4 *g, float4 *s) {
-    if (GEOM != GEOM_HULL) return nullptr;
+    if (URGYM_BASE(GEOM) != GEOM_HULL) return nullptr;
     for (int i = threadIdx.x; i < UR5E_NUM_HULL_VERTS; i += blockDim.x) s[i] = g[i];
     return s;
 }
@@ -172,7 +172,7 @@ template <int TASK> struct TileFloats {
 };
 template <int TASK, int GEOM> constexpr size_t step_smem_bytes() {
     return (size_t)URGYM_BLOCK * TileFloats<TASK>::value * sizeof(float) +
-           (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
+           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
 __device__ __forceinline__ void stat_add(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }   // RED.E.ADD.64 (result unused)
 
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK, URGYM_STEP_MINBLOCKS) urgym_step_
         }
     }
     const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
-    if (GEOM == GEOM_HULL) __syncthreads();
+    if (URGYM_BASE(GEOM) == GEOM_HULL) __syncthreads();
 
     const int64_t wbase = (int64_t)blockIdx.x * B + warp * W;                 // first env of this warp
     if (wbase >= A.n) return;
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_c
     int *s_k_all = s_list_all + NW * URGYM_RESET_GROUP;                      // [NW][GROUP] first iteration to evaluate
     float4 *s_hull = reinterpret_cast<float4 *>(s_k_all + NW * URGYM_RESET_GROUP);
     const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
-    if (GEOM == GEOM_HULL) __syncthreads();
+    if (URGYM_BASE(GEOM) == GEOM_HULL) __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *s_rows = s_rows_all + warp * W * D;
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(URGYM_AUTORESET_BLOCK) urgym_autoreset_kernel(
     int *s_k_all = s_list_all + NW * W;                                      // [NW][32]
     float4 *s_hull = reinterpret_cast<float4 *>(s_k_all + NW * W);
     const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
-    if (GEOM == GEOM_HULL) __syncthreads();
+    if (URGYM_BASE(GEOM) == GEOM_HULL) __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *s_rows = s_rows_all + warp * W * D;
@@ -543,11 +543,11 @@ __global__ void __launch_bounds__(URGYM_AUTORESET_BLOCK) urgym_autoreset_kernel(
 }
 template <int TASK, int GEOM> constexpr size_t autoreset_smem_bytes() {
     return (size_t)URGYM_AUTORESET_BLOCK * Traits<TASK>::OBS * sizeof(float) + 2 * URGYM_AUTORESET_BLOCK * sizeof(int) +
-           (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
+           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
 template <int TASK, int GEOM> constexpr size_t reset_smem_bytes() {
     return (size_t)URGYM_BLOCK * Traits<TASK>::OBS * sizeof(float) + 2 * (URGYM_BLOCK / 32) * URGYM_RESET_GROUP * sizeof(int) +
-           (GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
+           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
 }
 
 // every chain's reset-event counter := max over the chains + add.  add = 1: a reset event of its own (explicit reset,
@@ -600,7 +600,7 @@ template <int TASK, int GEOM>
 __global__ void __launch_bounds__(URGYM_BLOCK) urgym_refresh_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
     extern __shared__ float4 smem4[];
     const float4 *hv = stage_hull<GEOM>(A.hull, smem4);
-    if (GEOM == GEOM_HULL) __syncthreads();
+    if (URGYM_BASE(GEOM) == GEOM_HULL) __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * URGYM_BLOCK + threadIdx.x;
     if (i >= A.n) return;
     EnvState s;
@@ -641,7 +641,7 @@ template <int TASK, int GEOM> cudaError_t launch_autoreset(const ModelConst &M, 
     return cudaLaunchKernelEx(&cfg, urgym_autoreset_kernel<TASK, GEOM>, M, A);
 }
 template <int TASK, int GEOM> cudaError_t launch_refresh(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
-    const size_t smem = GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
+    const size_t smem = URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
     urgym_refresh_kernel<TASK, GEOM><<<grid_for(A.n), URGYM_BLOCK, smem, s>>>(M, A);
     return cudaGetLastError();
 }
@@ -654,7 +654,7 @@ template <int TASK, int GEOM> cudaError_t prepare_kernels(const ModelConst &, co
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(urgym_autoreset_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)autoreset_smem_bytes<TASK, GEOM>());
     if (e != cudaSuccess) return e;
-    const size_t smem = GEOM == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
+    const size_t smem = URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
     if (smem) e = cudaFuncSetAttribute(urgym_refresh_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     return e;
 }
@@ -682,3 +682,6 @@ typedef cudaError_t (*aux_launcher_t)(const ModelConst &, const AuxArgs &, cudaS
     cudaError_t urgym_inst_prepare_##T##_##G(const ModelConst &, const AuxArgs &, cudaStream_t);
 URGYM_DECLARE_INST(0, 0) URGYM_DECLARE_INST(1, 0) URGYM_DECLARE_INST(2, 0) URGYM_DECLARE_INST(3, 0)
 URGYM_DECLARE_INST(0, 1) URGYM_DECLARE_INST(1, 1) URGYM_DECLARE_INST(2, 1) URGYM_DECLARE_INST(3, 1)
+// link-distance mode "workbench" (GEOM | GEOM_WB); UR5OriReach has no link_dist
+URGYM_DECLARE_INST(1, 2) URGYM_DECLARE_INST(2, 2) URGYM_DECLARE_INST(3, 2)
+URGYM_DECLARE_INST(1, 3) URGYM_DECLARE_INST(2, 3) URGYM_DECLARE_INST(3, 3)
