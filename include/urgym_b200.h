@@ -150,6 +150,15 @@ int urgym_step_host(urgym_env_t *h, const float *actions, float *obs, float *ach
                     float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
                     float *terminal_obs, float *terminal_achieved);
 int urgym_reset_host(urgym_env_t *h, const uint8_t *mask, float *obs, float *achieved, float *desired);
+/* The same step without the final wait, for callers that keep two sets of (pinned) host buffers: step k goes into
+ * `slot` k % 2 and the call returns as soon as everything is enqueued; urgym_host_wait(h, slot) blocks until that slot's
+ * results are complete in host memory.  Enqueueing step k + 1 (other slot) before waiting for step k lets its kernels run
+ * under step k's device-to-host copies.  A slot must be waited for before it is used again (URGYM_EINVAL otherwise), and
+ * its `actions` buffer must stay untouched until then.  Do not mix with urgym_step_host while a slot is in flight. */
+int urgym_step_host_async(urgym_env_t *h, int slot, const float *actions, float *obs, float *achieved, float *desired,
+                          float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
+                          float *terminal_obs, float *terminal_achieved);
+int urgym_host_wait(urgym_env_t *h, int slot);
 
 /* ---- options / checkpoint scalars ---------------------------------------------------------------------------- */
 /* auto-reset on (default, DummyVecEnv semantics) or off (a bare RobotTaskEnv: finished envs keep their state and

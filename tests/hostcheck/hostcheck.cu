@@ -161,12 +161,6 @@ void hc_set_obstacle(float r, float h, float margin) {
     g_M.obst_r = r; g_M.obst_h = h; g_M.obst_margin = margin;
 }
 void hc_set_ld_mode(int mode) { g_ld_mode = mode; }
-#ifdef URGYM_HC_COUNTERS
-void hc_counters(unsigned long long *out) {     // 10 slow, 10 slow hits, 10 probe hits, 10 aabb rejects, 9 need
-    for (int k = 0; k < 10; k++) { out[k] = g_hc_slow[k]; out[10 + k] = g_hc_slow_hit[k]; out[20 + k] = g_hc_probe_hit[k]; out[30 + k] = g_hc_aabb_rej[k]; }
-    for (int k = 0; k < 9; k++) out[40 + k] = g_hc_need[k];
-}
-#endif
 void hc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
     uint4 r = philox4x32_10(make_uint4(c[0], c[1], c[2], c[3]), make_uint2(k[0], k[1]));
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;

@@ -466,7 +466,9 @@ def test_sta_moving_obstacle_injection(geom, ug):
         for i, e in enumerate(orc.envs):
             e.task.set_goal_and_obstacle(sc[i].astype(np.float64))
 
-    kw = dict(ld_tol=5e-5, rew_atol=1e-2) if geom == oe.GEOM_HULL else {}
+    # (hull: a tilting cylinder brings its rims to the links more often than the static scenes do; FP32 GJK against a rim
+    # converges sublinearly)
+    kw = dict(ld_tol=1e-4, rew_atol=1e-2) if geom == oe.GEOM_HULL else {}
     st = run_parity(GpuSim("UR5StaReach-v1", geom, n, seed=8, offset=40), "UR5StaReach-v1", geom, n, steps, seed=8, offset=40,
                     action_scale=0.6, after_reset=inject, **kw)
     assert st["steps"] > 0.8 * n * steps and st["resets"] > 0, st

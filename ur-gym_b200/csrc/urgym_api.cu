@@ -99,6 +99,13 @@ struct urgym_env {
     cudaEvent_t ev_fork, ev_join[3];
     void *dstage;
     size_t dstage_bytes;
+    // asynchronous host-buffer step: two output slots, each with its own device staging and copy-out stream
+    void *aslot[2];
+    size_t aslot_bytes[2];
+    cudaStream_t ostream[2];
+    cudaEvent_t ev_chunk[2][16];     // step kernels of chunk c (slot s) done -> the copy-out stream may read them
+    cudaEvent_t ev_out[2];           // copy-out of slot s complete (the next step into slot s waits for it)
+    int aslot_busy[2];
     // kernel timing (urgym_profile_enable): event triples around the step and auto-reset kernels
     int profiling, prof_n;
     cudaEvent_t prof_ev[256][3];
@@ -258,6 +265,12 @@ extern "C" int urgym_destroy(urgym_env_t *h) {
         for (int k = 0; k < 256; k++)
             for (int j = 0; j < 3; j++) if (h->prof_ev[k][j]) cudaEventDestroy(h->prof_ev[k][j]);
     if (h->dstage) cudaFree(h->dstage);
+    for (int k = 0; k < 2; k++) {
+        if (h->aslot[k]) cudaFree(h->aslot[k]);
+        if (h->ostream[k]) cudaStreamDestroy(h->ostream[k]);
+        if (h->ev_out[k]) cudaEventDestroy(h->ev_out[k]);
+        for (int c = 0; c < 16; c++) if (h->ev_chunk[k][c]) cudaEventDestroy(h->ev_chunk[k][c]);
+    }
     if (h->hull) cudaFree(h->hull);
     if (h->pool) cudaFree(h->pool);
     delete h;
@@ -563,6 +576,100 @@ extern "C" int urgym_step_host(urgym_env_t *h, const float *actions, float *obs,
         if (terminal_achieved) CK(cudaMemcpyAsync(terminal_achieved + first * G, d_tach + first * G, (size_t)cnt * G * 4, cudaMemcpyDeviceToHost, s));
     }
     for (int j = 0; j < used; j++) CK(cudaStreamSynchronize(h->cstream[j]));
+    return URGYM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ asynchronous host step
+// Two output slots.  Step k goes into slot k % 2: actions host -> device and the step kernels run on the chunk streams (as
+// in urgym_step_host), the results leave on the slot's own copy-out stream, which waits for each chunk's kernels by event.
+// The call returns without waiting; while slot s drains over PCIe the caller may already enqueue the next step into
+// the other slot, whose kernels then run under this slot's device-to-host copies.
+static int ensure_async(urgym_env *h, int slot, size_t bytes) {
+    if (!h->ostream[slot]) {
+        CK(cudaStreamCreateWithFlags(&h->ostream[slot], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_out[slot], cudaEventDisableTiming));
+        for (int c = 0; c < 16; c++) CK(cudaEventCreateWithFlags(&h->ev_chunk[slot][c], cudaEventDisableTiming));
+    }
+    if (h->aslot_bytes[slot] >= bytes) return URGYM_OK;
+    if (h->aslot[slot]) { cudaFree(h->aslot[slot]); h->aslot[slot] = nullptr; h->aslot_bytes[slot] = 0; }
+    CK(cudaMalloc(&h->aslot[slot], bytes));
+    h->aslot_bytes[slot] = bytes;
+    return URGYM_OK;
+}
+
+extern "C" int urgym_step_host_async(urgym_env_t *h, int slot, const float *actions, float *obs, float *achieved, float *desired,
+                                     float *reward, uint8_t *terminated, uint8_t *truncated, uint8_t *is_success,
+                                     float *terminal_obs, float *terminal_achieved) {
+    if (!h) return URGYM_EINVAL;
+    if (slot != 0 && slot != 1) return fail(h, URGYM_EINVAL, "urgym_step_host_async: slot must be 0 or 1%s", "");
+    if (!actions || !obs || !reward || !terminated || !truncated || !is_success)
+        return fail(h, URGYM_EINVAL, "urgym_step_host_async: actions, obs, reward, terminated, truncated, is_success must not be NULL%s", "");
+    if (h->aslot_busy[slot])
+        return fail(h, URGYM_EINVAL, "urgym_step_host_async: slot still in flight, call urgym_host_wait(slot) first%s", "");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n, D = obs_dim(h->task), G = goal_dim(h->task);
+    const size_t b_act = align_up(n * 6 * 4, 256), b_obs = align_up(n * D * 4, 256), b_g = align_up(n * G * 4, 256),
+                 b_r = align_up(n * 4, 256), b_f = align_up(n, 256);
+    int rc = ensure_async(h, slot, b_act + 2 * b_obs + 3 * b_g + b_r + 3 * b_f);
+    if (rc != URGYM_OK) return rc;
+    char *p = (char *)h->aslot[slot];
+    float *d_act = (float *)p; p += b_act;
+    float *d_obs = (float *)p; p += b_obs;
+    float *d_tobs = (float *)p; p += b_obs;
+    float *d_ach = (float *)p; p += b_g;
+    float *d_des = (float *)p; p += b_g;
+    float *d_tach = (float *)p; p += b_g;
+    float *d_rew = (float *)p; p += b_r;
+    uint8_t *d_term = (uint8_t *)p; p += b_f;
+    uint8_t *d_trunc = (uint8_t *)p; p += b_f;
+    uint8_t *d_succ = (uint8_t *)p; p += b_f;
+    const int64_t N = h->n;
+    int64_t chunk = ((N / 8 + 255) / 256) * 256;
+    if (chunk < 65536) chunk = N;
+    cudaStream_t s0 = h->hstream, so = h->ostream[slot];
+    urgym_bump_kernel<<<1, 1, 0, s0>>>(h->d_event, 1u);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaEventRecord(h->ev_fork, s0));
+    int k = 0;
+    for (int64_t first = 0; first < N; first += chunk, k++) {
+        const int64_t cnt = (N - first) < chunk ? (N - first) : chunk;
+        cudaStream_t s = h->cstream[k % 3];
+        if (k < 3) CK(cudaStreamWaitEvent(s, h->ev_fork, 0));
+        CK(cudaMemcpyAsync(d_act + first * 6, actions + first * 6, (size_t)cnt * 6 * 4, cudaMemcpyHostToDevice, s));
+        rc = step_range(h, first, cnt, 0, 0, k % 3, d_act, d_obs, achieved ? d_ach : nullptr, desired ? d_des : nullptr, d_rew, d_term,
+                        d_trunc, d_succ, terminal_obs ? d_tobs : nullptr, terminal_achieved ? d_tach : nullptr, s);
+        if (rc != URGYM_OK) return rc;
+        CK(cudaEventRecord(h->ev_chunk[slot][k & 15], s));
+        CK(cudaStreamWaitEvent(so, h->ev_chunk[slot][k & 15], 0));
+        CK(cudaMemcpyAsync(obs + first * D, d_obs + first * D, (size_t)cnt * D * 4, cudaMemcpyDeviceToHost, so));
+        if (achieved) CK(cudaMemcpyAsync(achieved + first * G, d_ach + first * G, (size_t)cnt * G * 4, cudaMemcpyDeviceToHost, so));
+        if (desired) CK(cudaMemcpyAsync(desired + first * G, d_des + first * G, (size_t)cnt * G * 4, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(reward + first, d_rew + first, (size_t)cnt * 4, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(terminated + first, d_term + first, (size_t)cnt, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(truncated + first, d_trunc + first, (size_t)cnt, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(is_success + first, d_succ + first, (size_t)cnt, cudaMemcpyDeviceToHost, so));
+        if (terminal_obs) CK(cudaMemcpyAsync(terminal_obs + first * D, d_tobs + first * D, (size_t)cnt * D * 4, cudaMemcpyDeviceToHost, so));
+        if (terminal_achieved) CK(cudaMemcpyAsync(terminal_achieved + first * G, d_tach + first * G, (size_t)cnt * G * 4, cudaMemcpyDeviceToHost, so));
+    }
+    CK(cudaEventRecord(h->ev_out[slot], so));
+    // the next step's bump (on hstream) must follow this step's kernels: join the chunk streams back into hstream
+    for (int j = 0; j < 3 && j < k; j++) {
+        CK(cudaEventRecord(h->ev_join[j], h->cstream[j]));
+        CK(cudaStreamWaitEvent(s0, h->ev_join[j], 0));
+    }
+    h->aslot_busy[slot] = 1;
+    return URGYM_OK;
+}
+
+extern "C" int urgym_host_wait(urgym_env_t *h, int slot) {
+    if (!h) return URGYM_EINVAL;
+    if (slot != 0 && slot != 1) return fail(h, URGYM_EINVAL, "urgym_host_wait: slot must be 0 or 1%s", "");
+    if (!h->aslot_busy[slot]) return URGYM_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev_out[slot]));
+    h->aslot_busy[slot] = 0;
     return URGYM_OK;
 }
 

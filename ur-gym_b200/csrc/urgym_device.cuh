@@ -120,6 +120,9 @@ struct alignas(16) ModelConst {
     // table / track limits per (link, box), precomputed for the branch-free test of robot_pass_capsule:
     //   [0] zthr = top + reach   [1] cx  [2] cy  [3] hx | [4] hy  [5] xlo = cx - hx - reach  [6] xhi  [7] ylo | [8] yhi
     float box_lim[7][2][12];
+    // upper arm (link 2) vs table / track: constants of the separating-axis filter of robot_pass_capsule:
+    //   [0] cx  [1] cz  [2] hx  [3] hz  [4] reach = margin + fit_box[2] + box margin
+    float sat2[2][8];
     // packed-math copies (first, so that the pairs sit 8-byte aligned in the constant bank)
     float joint_rot_p[6][3][4]; // rows of joint_rot padded to 4: (F[k][0], F[k][1]) is a constant pair
     float cap_pp[7][3][2];      // (cap_p0[l][k], cap_p1[l][k])

@@ -195,11 +195,11 @@ URGYM_HD void twist_pose(const float *p0, Quat qs, const float *tw, int moved, O
     O.u = quat_axis_z(O.q);
     euler = euler_from_quat(O.q);
 }
-// ReachSta with a moving obstacle (injection-only path): rare, kept out of the hot instruction stream
-static URGYM_OOL void sta_moving_pose(const float *E, const float *C, int steps, ObstW &O, float3 &euler) {
-    const int m = (int)C[4];
-    Quat qs; qs.x = C[5]; qs.y = C[6]; qs.z = C[7]; qs.w = C[8];
-    twist_pose(&E[6], qs, &C[9], steps < m ? steps : m, O, euler);
+// ReachSta with a moving obstacle (injection-only path): rare.  Out of line, and called with VALUES: handing it pointers
+// into the env's E / C words would force those arrays into local memory for the whole step kernel.
+struct StaMotion { float p0[3], tw[6]; Quat qs; int m; };
+static URGYM_OOL void sta_moving_pose(StaMotion mo, int steps, ObstW &O, float3 &euler) {
+    twist_pose(mo.p0, mo.qs, mo.tw, steps < mo.m ? steps : mo.m, O, euler);
 }
 // `steps`: env steps of the episode the obstacle has been through (capped inside: Dyn moves for 25, reach.py:735)
 template <int TASK> URGYM_HD ObstW obstacle_cached(const float *E, const float *C, int steps, float3 &euler) {
@@ -213,7 +213,15 @@ template <int TASK> URGYM_HD ObstW obstacle_cached(const float *E, const float *
             O.c = f3(E[6], E[7], E[8]); O.u = f3(C[5], C[6], C[7]);
             euler = f3(C[8], C[9], C[10]);
         } else {
-            sta_moving_pose(E, C, steps, O, euler);
+            StaMotion mo;
+            mo.p0[0] = E[6]; mo.p0[1] = E[7]; mo.p0[2] = E[8];
+            mo.qs.x = C[5]; mo.qs.y = C[6]; mo.qs.z = C[7]; mo.qs.w = C[8];
+#pragma unroll
+            for (int k = 0; k < 6; k++) mo.tw[k] = C[9 + k];
+            mo.m = (int)C[4];
+            ObstW Om; float3 em;
+            sta_moving_pose(mo, steps, Om, em);
+            O = Om; euler = em;
         }
     } else if (TASK == TASK_DYN) {
         const int moved = steps < 25 ? steps : 25;
@@ -441,9 +449,6 @@ URGYM_HD bool robot_pass_rolled(const ModelConst &M, const float *qrow, const Ob
 // link pairs, so each distance routine exists once in the instruction stream.
 // scratch layout: 36 floats capsule endpoints (link 1..6: a.xyz b.xyz), 5 floats link-obstacle distances.
 #define URGYM_SCRATCH_FLOATS 41
-#ifdef URGYM_HC_COUNTERS
-static unsigned long long g_hc_slow[10], g_hc_slow_hit[10], g_hc_probe_hit[10], g_hc_aabb_rej[10], g_hc_need[9];
-#endif
 // link-distance mode "workbench": fold the link's distances to the table and the track into the link-obstacle
 // distances of the scratch column
 static URGYM_OOL void workbench_link_dist(const ModelConst &M, float *cap, int cs) {
@@ -496,6 +501,21 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
             const bool a_low = a.z <= b.z;
             const float Lx = a_low ? a.x : b.x, Ly = a_low ? a.y : b.y, zmin = fminf(a.z, b.z);
             const float minx = fminf(a.x, b.x), maxx = fmaxf(a.x, b.x), miny = fminf(a.y, b.y), maxy = fmaxf(a.y, b.y);
+            // Upper arm only (a warp-uniform branch): in steady state three quarters of the `slow` cases are the upper arm
+            // hanging down beside the track or behind the table, and 87 % of those are no hits.  The axis n = d x e_y
+            // (perpendicular to the segment and to the boxes' long edges) separates every one of them: the segment
+            // projects to a point, the box to |n_x| hx + |n_z| hz, and a gap beyond `reach` is a proven miss.
+            bool apart[2] = {false, false};
+            if (l == 2) {
+                const float dx = b.x - a.x, dz = b.z - a.z, mx = 0.5f * (a.x + b.x), mz = 0.5f * (a.z + b.z);
+                const float nn = sqrtf(fmaf(dx, dx, dz * dz));
+#pragma unroll
+                for (int box = 0; box < 2; box++) {
+                    const float *S = M.sat2[box];           // cx, cz, hx, hz, reach
+                    const float gap = fabsf(fmaf(dx, mz - S[1], -dz * (mx - S[0]))) - fmaf(S[2], fabsf(dz), S[3] * fabsf(dx));
+                    apart[box] = gap > S[4] * nn;
+                }
+            }
 #pragma unroll
             for (int box = 0; box < 2; box++) {
                 const float *L = M.box_lim[l][box];         // zthr, cx, cy, hx, hy, xlo, xhi, ylo, yhi
@@ -503,32 +523,25 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
                 const bool over = fabsf(Lx - L[1]) <= L[3] && fabsf(Ly - L[2]) <= L[4];
                 const bool beside = maxx >= L[5] && minx <= L[6] && maxy >= L[7] && miny <= L[8];
                 hit = hit || (near_z && over);
-                if (near_z && !over && beside) slow |= 1u << (2 * (l - 2) + box);
+                if (near_z && !over && beside && !apart[box]) slow |= 1u << (2 * (l - 2) + box);
             }
         }
     }
     while (slow) {          // exact segment-box distance for the few (link, box) cases left
         const int k = __ffs_hd(slow) - 1;
-#ifdef URGYM_HC_COUNTERS
-        g_hc_slow[k]++;
-#endif
         slow &= slow - 1u;
         const int l = 2 + (k >> 1), box = k & 1;
         const float *c = cap + (l - 1) * 6 * cs;
         const float3 a = f3(c[0], c[cs], c[2 * cs]), b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
         const float3 bc = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
         const float3 bh = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
-        hit = hit || (sqrtf(seg_box_dist2(a, b, bc, bh)) - M.fit_box[l] - M.box_margin[box] <= URGYM_COLLISION_MARGIN);
-#ifdef URGYM_HC_COUNTERS
-        if (sqrtf(seg_box_dist2(a, b, bc, bh)) - M.fit_box[l] - M.box_margin[box] <= URGYM_COLLISION_MARGIN) g_hc_slow_hit[k]++;
-        {   // would a 3-point probe have decided it?
-            float reach = URGYM_COLLISION_MARGIN + M.fit_box[l] + M.box_margin[box];
-            float3 m = 0.5f * (a + b);
-            float pm = fminf(fminf(point_box_dist2(a, bc, bh), point_box_dist2(b, bc, bh)), point_box_dist2(m, bc, bh));
-            if (pm <= reach * reach) g_hc_probe_hit[k]++;
-            if (seg_box_lower2(a, b, bc, bh) > reach * reach) g_hc_aabb_rej[k]++;
-        }
+#ifdef URGYM_SLOW_PROBE
+        // most of what is left are hits, and for most hits an end point or the midpoint is already within reach
+        const float reach = URGYM_COLLISION_MARGIN + M.fit_box[l] + M.box_margin[box];
+        const float pr = fminf(fminf(point_box_dist2(a, bc, bh), point_box_dist2(b, bc, bh)), point_box_dist2(0.5f * (a + b), bc, bh));
+        if (pr <= reach * reach) { hit = true; continue; }
 #endif
+        hit = hit || (sqrtf(seg_box_dist2(a, b, bc, bh)) - M.fit_box[l] - M.box_margin[box] <= URGYM_COLLISION_MARGIN);
     }
     // self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6), pair index p = 0..8 in that order: a broad phase for all nine with static
     // indices, then the exact segment-segment test only for the pairs it leaves, in a rolled loop.
@@ -567,9 +580,6 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
         }
         while (need) {
             const int p = __ffs_hd(need) - 1;
-#ifdef URGYM_HC_COUNTERS
-            g_hc_need[p]++;
-#endif
             need &= need - 1u;
             const int l1 = p < 4 ? 1 : (p < 7 ? 2 : 3);
             const int l2 = p < 4 ? p + 3 : (p < 7 ? p : p - 2);

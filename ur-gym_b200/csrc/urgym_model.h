@@ -99,6 +99,11 @@ static void build_model_const(ModelConst &M) {
             L[0] = M.box_c[b][2] + M.box_he[b][2] + reach; L[1] = cx; L[2] = cy; L[3] = hx; L[4] = hy;
             L[5] = cx - hx - reach; L[6] = cx + hx + reach; L[7] = cy - hy - reach; L[8] = cy + hy + reach;
         }
+    for (int b = 0; b < 2; b++) {
+        float *S = M.sat2[b];
+        S[0] = M.box_c[b][0]; S[1] = M.box_c[b][2]; S[2] = M.box_he[b][0]; S[3] = M.box_he[b][2];
+        S[4] = 0.01f + M.fit_box[2] + M.box_margin[b];
+    }
     M.fit_obst_h = (float)URGYM_FIT_OBST_H;
     M.fit_obst_ie = (float)(1.0 / (4.0 * URGYM_FIT_OBST_H * URGYM_FIT_OBST_H));
     M.box_top = (float)fmax(tc[2] + th[2] - pm, kc[2] + kh[2] - pm);

@@ -285,6 +285,17 @@ class UR5VecEnv:
                                                  _ptr(out.get("terminal_obs")), None))
         return out
 
+    def step_host_async(self, slot: int, actions, out: Dict[str, torch.Tensor]) -> None:
+        """enqueue a host-buffer step into output slot 0 / 1 and return at once (urgym_step_host_async); `out` and
+        `actions` belong to the slot until host_wait(slot) returns"""
+        self._need_reset()
+        nat.check(self.h, self.L.urgym_step_host_async(self.h, int(slot), _ptr(actions), _ptr(out["obs"]), None, None,
+                                                       _ptr(out["reward"]), _ptr(out["terminated"]), _ptr(out["truncated"]),
+                                                       _ptr(out["is_success"]), _ptr(out.get("terminal_obs")), None))
+
+    def host_wait(self, slot: int) -> None:
+        nat.check(self.h, self.L.urgym_host_wait(self.h, int(slot)))
+
     def alloc_host_buffers(self, terminal_obs: bool = True, pin: bool = True) -> Dict[str, torch.Tensor]:
         n, D = self.num_envs, self.obs_dim
         mk = lambda shape, dt: torch.zeros(shape, dtype=dt, pin_memory=pin)
