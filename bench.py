@@ -37,7 +37,9 @@ def parse():
     ap.add_argument("--geometry", default="capsule", choices=["capsule", "hull"])
     ap.add_argument("--chains", type=int, default=2, help="independent env sub-ranges per GPU in the captured graph (1..8)")
     ap.add_argument("--graph-steps", type=int, default=32, help="env steps captured per CUDA graph replay (multiple of 8)")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=60)
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
+    ap.add_argument("--no-extra-configs", action="store_true", help="headline only: skip the other BASELINE configs / rollout loop")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall-clock budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -115,7 +117,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": dict(workload_config(args, world), env_steps_per_bench_step=procs * sample,
+                           note="one bench step of this arm = `env_steps_per_bench_step` env steps (a bounded sample of the "
+                                "workload on the host cores): value = env_steps_per_bench_step / (ms_per_step / 1000)"),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
                              "sample": f"{procs} processes x {sample * max(args.steps, 1)} env steps of {args.task} (one oracle env per "
                                        "process, reset on done); the reference itself needs PyBullet, which is not installable "
@@ -167,40 +171,68 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    import urgym_b200 as ug
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and therefore the pages of the pinned host buffers it allocates afterwards) to the CPUs of the
+    NUMA node its GPU hangs off.  Eight ranks that all sit on node 0 push every host copy of the far GPUs across the
+    socket interconnect (round 1: e2e scaling efficiency 0.23 at N = 8)."""
+    info = {"bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = sorted(cpus & allowed)
+        info.update({"pci": bdf, "numa_node": node, "local_cpulist": cpulist})
+        if node >= 0 and use:
+            os.sched_setaffinity(0, use)
+            info.update({"bound": True, "cpus": len(use)})
+    except Exception as e:                           # not fatal: the numbers are then measured unbound, and say so
+        info["error"] = repr(e)
+    return info
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the simulator has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    saved_stdout = None
-    if world > 1:
-        # NCCL prints its version banner on stdout; the contract is ONE JSON line there, so everything but the final
-        # print goes to stderr
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    n = args.envs_per_gpu
-    env = ug.UR5VecEnv(args.task, n, device=local_rank, seed=0, env_index_offset=rank * n, geometry=args.geometry,
-                       goal_buffers=True)
+
+def pinned_copy_bandwidth(dev, mbytes=256, reps=5):
+    """GB/s of one pinned-host <-> device cudaMemcpyAsync of `mbytes`, best of `reps`, each direction: the ceiling of the
+    end-to-end path on this box, measured live (e2e.roofline.peak)."""
+    import torch
+    n = mbytes * (1 << 20)
+    host, devb = torch.empty(n, dtype=torch.uint8, pin_memory=True), torch.empty(n, dtype=torch.uint8, device=dev)
+    best = {}
+    for name, (dst, src) in {"d2h": (host, devb), "h2d": (devb, host)}.items():
+        t = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); dst.copy_(src, non_blocking=True); e1.record(); torch.cuda.synchronize(dev)
+            t.append(e0.elapsed_time(e1))
+        best[name] = n / (min(t) * 1e-3) / 1e9
+    return best
+
+
+def measure_device(ug, torch, dist, dev, local_rank, rank, world, task, n, geometry, steps, warm, chains, gs, offset,
+                   link_dist="obstacle"):
+    """One device-resident measurement: env-steps/s of `task` with n envs on this rank (inputs resident in HBM), max over
+    ranks, plus the live per-kernel event timings.  Returns the dict that becomes a bench line or a `configs` entry."""
+    import ctypes
+    env = ug.UR5VecEnv(task, n, device=local_rank, seed=0, env_index_offset=offset, geometry=geometry, goal_buffers=True,
+                       link_dist=link_dist)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     ring = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(8)]
     env.reset()
-    warm = max(args.warmup, 3)
     for k in range(warm):
         env.step(ring[k % 8])
-    # the timed loop replays a CUDA graph of 8 steps (one per action buffer of the ring): 2 kernels per step and chain
-    chains = args.chains if n >= (1 << 19) else 1       # small batches: sub-ranges would not fill the 148 SMs
-    gs = max(8, args.graph_steps // 8 * 8)
+    chains = chains if n >= (1 << 19) else 1         # small batches: sub-ranges would not fill the 148 SMs
+    gs = max(8, min(gs, max(steps, 8)) // 8 * 8)
     graph = env.capture_steps(ring * (gs // 8), chains=chains)
     graph.replay()
     env.stats(reset=True)
-    steps = max(args.steps, 1)
-    n_replays, rem = divmod(steps, gs)                # exactly `steps` env steps: whole replays + a shorter graph
+    n_replays, rem = divmod(steps, gs)               # exactly `steps` env steps: whole replays + a shorter graph
     graph_rem = env.capture_steps([ring[k % 8] for k in range(rem)], chains=chains) if rem else None
     if graph_rem is not None:
         graph_rem.replay()
@@ -224,17 +256,15 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
-    st = env.stats(reset=True)                        # episodes finished inside the timed region only
+    st = env.stats(reset=True)                       # episodes finished inside the timed region only
     clock_note = "sampled during the timed region (NVML, 5 ms period)"
     if len(sampler.samples) < 8:
-        # the timed region was too short for the 5 ms sampler: keep sampling over an untimed repeat of the same loop
-        t_end = time.perf_counter() + 0.25
+        t_end = time.perf_counter() + 0.25           # too short for the 5 ms sampler: an untimed repeat of the same loop
         while time.perf_counter() < t_end:
             graph.replay()
             torch.cuda.synchronize(dev)
         clock_note = "timed region shorter than the sampler period: sampled during an untimed 0.25 s repeat of the same loop"
     sampler.stop_flag = True
-    launches = 2 * steps * chains                     # step kernel + auto-reset kernel per env step and chain
     barrier()
     env.stats(reset=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -242,11 +272,8 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         st = ug.allreduce_stats(st, device=dev)
     ms_max = float(t.item())
-    value = n * world * steps / (ms_max * 1e-3)
-
-    # per-kernel durations, measured live with CUDA events recorded by the library on the launching stream directly
-    # around each kernel (urgym_profile_enable), over a queue of back-to-back eager steps (one chain, serial kernels)
-    import ctypes
+    # per-kernel durations: CUDA events recorded by the library on the launching stream directly around each kernel
+    # (urgym_profile_enable), over back-to-back eager steps (one chain, serial kernels)
     ks = max(8, min(64, steps))
     env.L.urgym_profile_enable(env.h, 1)
     for k in range(ks):
@@ -255,58 +282,204 @@ def run_ours(args, rank, world, local_rank):
     env.L.urgym_profile_read(env.h, ctypes.byref(a_ms), ctypes.byref(b_ms), ctypes.byref(cnt))
     env.L.urgym_profile_enable(env.h, 0)
     env.stats(reset=True)
-    t_step_kernel, t_reset_kernel = a_ms.value, b_ms.value          # ms
+    return dict(env=env, ring=ring, ms=ms, ms_max=ms_max, steps=steps, stats=st, chains=chains, graph_steps=gs,
+                kernel_ms=a_ms.value, reset_kernel_ms=b_ms.value, clocks=dict(sampler.result(), how=clock_note),
+                value=n * world * steps / (ms_max * 1e-3), launches=2 * steps * chains + (steps // gs + (1 if rem else 0)) * (chains > 1))
 
-    # roofline: algorithmic bytes per launch / that kernel's average launch duration
-    peaks = {}
+
+def load_peaks():
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def roofline_of(m, task, n, world, geometry):
+    """algorithmic bytes per launch / that kernel's average launch duration (capsule geometry, HBM-bound by
+    construction); hull geometry is bound by the FP32 pipe and is reported against it."""
+    peaks = load_peaks()
+    steps, st = m["steps"], m["stats"]
+    resets_per_launch = st["episodes"] / world / steps
+    if geometry == "hull":
+        # every GJK support query scans the link's hull: 3 FMA per vertex.  The library counts the vertices it scans
+        # (urgym_stats slot 7 is reused by hull handles? no: see `hull_vertex_dots`), so the flops are the kernel's own
+        dots = st.get("hull_vertex_dots_per_step")
+        sm_max = peaks.get("sm_max_mhz", 1965.0)
+        peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12              # FP32 FMA pipe, TFLOP/s at the maximum SM clock
+        out = {"bound": "fp32", "peak": peak, "unit": "TFLOP/s", "peak_source": f"148 SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (nominal)",
+               "kernel": f"urgym_step_kernel<{task}, hull>: {n} env-steps per launch", "kernel_ms": m["kernel_ms"],
+               "reset_kernel_ms": m["reset_kernel_ms"], "traffic": None}
+        if dots:
+            ach = 6.0 * dots / (m["kernel_ms"] * 1e-3) / 1e12
+            out.update({"achieved": ach, "frac": ach / peak,
+                        "flops_per_launch": 6.0 * dots, "flops_how": "6 flop per hull vertex scanned by a GJK support query, counted by the kernel"})
+        else:
+            out.update({"achieved": None, "frac": None})
+        return out
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
+    achieved = n * BYTES_STEP[task] / (m["kernel_ms"] * 1e-3) / 1e9
+    whole = (n * BYTES_STEP[task] + resets_per_launch * BYTES_RESET[task]) / (m["ms"] * 1e-3 / steps) / 1e9
+    traffic, traffic_src = None, None
+    try:
+        summ = json.load(open(os.path.join(ROOT, "profiles", "ncu_step_kernel_summary.json")))
+        if n == summ.get("envs_per_launch", 1 << 20):
+            traffic, traffic_src = summ["dram_bytes_per_launch"].get(task), summ.get("source")
     except Exception:
         pass
-    peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
-    episodes_per_launch = st["episodes"] / world / steps
-    achieved = n * BYTES_STEP[args.task] / (t_step_kernel * 1e-3) / 1e9
-    whole = (n * BYTES_STEP[args.task] + episodes_per_launch * BYTES_RESET[args.task]) / (ms * 1e-3 / steps) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_step_kernel_summary.json")))["dram_bytes_per_launch"].get(args.task)
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback (B200_PROFILING.md)",
-                "kernel": f"urgym_step_kernel<{args.task}, {args.geometry}>: {n} env-steps per launch x {BYTES_STEP[args.task]} B",
-                "kernel_ms": t_step_kernel, "reset_kernel_ms": t_reset_kernel,
-                "bytes_per_env_step": BYTES_STEP[args.task], "bytes_per_reset": BYTES_RESET[args.task],
-                "resets_per_step": episodes_per_launch,
-                "whole_step": {"achieved": whole, "frac": whole / peak,
-                               "note": "step + auto-reset kernels: (N*B_step + N_done*B_reset) / (timed region / steps)"},
-                "note": "the kernel is bound by the SM issue rate, not by HBM (ncu, steady state: ~77 % issue-active with 75 % of the "
-                        "lanes doing work, DRAM ~37 %); see DESIGN.md section 5 and profiles/"}
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src, "peak_source": peak_src,
+            "kernel": f"urgym_step_kernel<{task}, {geometry}>: {n} env-steps per launch x {BYTES_STEP[task]} B",
+            "kernel_ms": m["kernel_ms"], "reset_kernel_ms": m["reset_kernel_ms"],
+            "bytes_per_env_step": BYTES_STEP[task], "bytes_per_reset": BYTES_RESET[task], "resets_per_step": resets_per_launch,
+            "whole_step": {"achieved": whole, "frac": whole / peak,
+                           "how": "step + auto-reset kernels: (N*B_step + N_done*B_reset) / (timed region / steps)"}}
 
-    # end to end through the host-buffer entry point: pinned host actions in, observations / rewards / flags out
-    buf = env.alloc_host_buffers(terminal_obs=False)
+
+def measure_e2e(torch, dist, dev, world, env, ring, n, task, steps):
+    """The same metric through the reference-facing host-buffer entry points: pinned host actions in, observation +
+    reward + flags out, every step; two output slots in flight (urgym_step_host_async / urgym_host_wait)."""
+    bufs = [env.alloc_host_buffers(terminal_obs=False) for _ in range(2)]
     host_ring = [r.cpu().pin_memory() for r in ring[:2]]
     for k in range(2):
-        env.step_host(host_ring[k % 2], buf)
-    barrier()
+        env.step_host(host_ring[k % 2], bufs[k % 2])
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
-    for k in range(args.e2e_steps):
-        env.step_host(host_ring[k % 2], buf)
+    env.step_host_async(0, host_ring[0], bufs[0])
+    for k in range(1, steps):
+        env.step_host_async(k % 2, host_ring[k % 2], bufs[k % 2])
+        env.host_wait((k - 1) % 2)                   # (a consumer would read slot (k - 1) % 2 here)
+    env.host_wait((steps - 1) % 2)
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    D = OBS_DIM[args.task]
-    e2e = {"value": n * world * args.e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 24,
-           "d2h_bytes_per_step": n * (4 * D + 4 + 3), "steps": args.e2e_steps,
-           "path": "urgym_step_host: pinned host actions -> device, step kernel, observation + reward + 3 flag arrays -> pinned host"}
+    dt = float(tt.item())
+    D = OBS_DIM[task]
+    h2d, d2h = n * 24, n * (4 * D + 4 + 3)
+    bw = pinned_copy_bandwidth(dev)
+    ach = (h2d + d2h) * steps / dt / 1e9
+    return {"value": n * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+            "path": "urgym_step_host_async / urgym_host_wait, two slots in flight: pinned host actions -> device, step + "
+                    "auto-reset kernels, observation + reward + 3 flag arrays -> pinned host",
+            "roofline": {"bound": "pcie", "achieved": ach, "unit": "GB/s per GPU (both directions summed)",
+                         "peak": bw["d2h"], "frac": ach / bw["d2h"], "peak_h2d": bw["h2d"],
+                         "peak_source": "one 256 MB pinned cudaMemcpyAsync device->host on this rank, best of 5, measured in this run "
+                                        "(all ranks copy at the same time only in the e2e loop itself)"}}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
-            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
-            "e2e": e2e, "gpu_launches": launches, "clocks": dict(sampler.result(), how=clock_note),
-            "episode_stats": ug.summarize(st)}
+
+def measure_rollout(ug, torch, dist, dev, world, m, task, n, steps):
+    """BASELINE config C5's wording: the envs "driving a SAC rollout loop" (train.py:39-60).  The shipped policy of the
+    task computes the actions from the observations on the device, the step follows, urgym_replay_write appends the
+    transitions to a device-resident ring; captured as CUDA graphs of 8 steps.  SAC's gradient step is the caller's."""
+    import numpy as np
+    short = {"UR5OriReach-v1": "Ori", "UR5ObsReach-v1": "Obs", "UR5StaReach-v1": "Sta", "UR5DynReach-v1": "Dyn"}[task]
+    w = np.load(os.path.join(ROOT, "tests", "golden", f"policy_{short}.npz"))
+    policy = ug.mlp_policy({k: torch.as_tensor(w[k], device=dev) for k in w.files if not k.startswith("published")}, torch.bfloat16)
+    env = m["env"]
+    ring = ug.DeviceReplayRing(env, capacity=4 * n)
+    noise = m["ring"]
+    k = [0]
+
+    def explore(obs):                                # SAC acts stochastically while it collects: policy mean + noise
+        k[0] += 1
+        return torch.clamp(policy(obs) + 0.3 * noise[k[0] % 8], -1.0, 1.0)
+
+    ro = ug.Rollout(env, explore, ring)
+    ro.capture(8)
+    ro.replay(2)
+    env.stats(reset=True)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    reps = max(1, steps // 8)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ro.replay(reps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = env.stats(reset=True)
+    if world > 1:
+        st = ug.allreduce_stats(st, device=dev)
+    ms = float(t.item())
+    D = OBS_DIM[task]
+    return {"value": n * world * reps * 8 / (ms * 1e-3), "unit": UNIT, "steps": reps * 8, "ms_per_step": ms / (reps * 8),
+            "what": "actor MLP (bf16 torch matmuls, the shipped policy + exploration noise) -> urgym_step -> urgym_replay_write "
+                    "into a device ring of 4 N transitions; CUDA graphs of 8 steps; no host traffic",
+            "replay_bytes_per_env_step": 2 * (2 * 4 * D + 24 + 4 + 2), "episode_stats": ug.summarize(st)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import urgym_b200 as ug
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the simulator has no CPU path (use --impl reference for the CPU arm)")
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False, "skipped": True}
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    saved_stdout = None
+    if world > 1:
+        # NCCL prints its version banner on stdout; the contract is ONE JSON line there, so everything but the final
+        # print goes to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    n = args.envs_per_gpu
+    steps, warm = max(args.steps, 1), max(args.warmup, 3)
+    m = measure_device(ug, torch, dist, dev, local_rank, rank, world, args.task, n, args.geometry, steps, warm, args.chains,
+                       args.graph_steps, rank * n)
+    roofline = roofline_of(m, args.task, n, world, args.geometry)
+    e2e = measure_e2e(torch, dist, dev, world, m["env"], m["ring"], n, args.task, max(args.e2e_steps, 2))
+    cfg = workload_config(args, world)
+    cfg.update({"chains_per_gpu": m["chains"], "graph_steps": m["graph_steps"], "numa": numa})
+    line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": m["ms_max"] / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "roofline": roofline,
+            "e2e": e2e, "gpu_launches": m["launches"], "clocks": m["clocks"],
+            "episode_stats": ug.summarize(m["stats"])}
+    if not args.no_extra_configs:
+        # the other BASELINE.json configs, measured the same way (shorter), and C5's rollout loop
+        extra = {}
+        if args.task == "UR5DynReach-v1" and args.geometry == "capsule":
+            try:
+                extra["C5_rollout_loop"] = dict(measure_rollout(ug, torch, dist, dev, world, m, args.task, n, 64),
+                                                config=f"{args.task}, {n} envs per GPU x {world} GPU(s), policy-driven, replay ring on the device")
+            except Exception as e:
+                extra["C5_rollout_loop"] = {"error": repr(e)}
+        m["env"].close()
+        todo = [("C2_Ori_65536", "UR5OriReach-v1", 65536, 1), ("C3_Obs_1Mi", "UR5ObsReach-v1", 1 << 20, 1)]
+        if world >= 2:
+            todo.append(("C4_Sta_4Mi_sharded", "UR5StaReach-v1", (4 << 20) // world, world))
+        for name, task, ne, need in todo:
+            try:
+                if need == 1 and world > 1:
+                    # single-GPU configs under torchrun: every rank runs its own copy, the line reports ONE GPU
+                    mm = measure_device(ug, torch, None, dev, local_rank, rank, 1, task, ne, "capsule", 104, 3, args.chains, 32, 0)
+                    w_eff = 1
+                else:
+                    mm = measure_device(ug, torch, dist, dev, local_rank, rank, world, task, ne, "capsule", 104, 3, args.chains, 32, rank * ne)
+                    w_eff = world
+                extra[name] = {"config": f"{task}, {ne} envs per GPU x {w_eff} GPU(s), capsule geometry, random actions",
+                               "value": mm["value"], "unit": UNIT, "n_gpus": w_eff, "steps": mm["steps"],
+                               "ms_per_step": mm["ms_max"] / mm["steps"], "roofline": roofline_of(mm, task, ne, w_eff, "capsule"),
+                               "episode_stats": ug.summarize(mm["stats"])}
+                if ne < (1 << 19):
+                    extra[name]["note"] = ("launch-bound: the per-step traffic of this batch fits the 126 MB L2, so the HBM fraction "
+                                           "is not a roofline statement here (SURVEY.md 7.3-5)")
+                mm["env"].close()
+            except Exception as e:
+                extra[name] = {"error": repr(e)}
+        if world < 2:
+            extra["C4_Sta_4Mi_sharded"] = {"skipped": "BASELINE.json shards this config over 2/4/8 GPUs; run with --gpus >= 2"}
+        line["configs"] = extra
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             procs = os.cpu_count() or 1

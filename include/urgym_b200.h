@@ -160,6 +160,20 @@ int urgym_step_host_async(urgym_env_t *h, int slot, const float *actions, float 
                           float *terminal_obs, float *terminal_achieved);
 int urgym_host_wait(urgym_env_t *h, int slot);
 
+/* ---- device-resident replay ring (the env side of train.py's SAC loop without leaving the GPU) --------------------- */
+/* Append one transition per env to caller-owned device rings of `capacity` rows (capacity >= N):
+ *   ring_obs / ring_next_obs [capacity, D], ring_actions [capacity, 6], ring_reward [capacity], ring_done,
+ *   ring_timeout [capacity] uint8.   Row (cursor + i) % capacity receives env i's (obs, action, reward, next_obs, done,
+ *   TimeLimit.truncated); next_obs is terminal_obs[i] where the env finished (SB3 VecEnv / ReplayBuffer semantics:
+ *   train.py:39-48 through DummyVecEnv).  `cursor` is a device-resident counter that the call advances by N, so a captured
+ *   CUDA graph of (policy, urgym_step, urgym_replay_write) keeps appending on every replay.
+ *   obs = the observation the actions were computed from; next_obs / terminal_obs / reward / flags = urgym_step's outputs. */
+int urgym_replay_write(urgym_env_t *h, const float *obs, const float *actions, const float *reward,
+                       const uint8_t *terminated, const uint8_t *truncated, const float *next_obs,
+                       const float *terminal_obs, float *ring_obs, float *ring_next_obs, float *ring_actions,
+                       float *ring_reward, uint8_t *ring_done, uint8_t *ring_timeout, int64_t capacity,
+                       unsigned long long *cursor, void *stream);
+
 /* ---- options / checkpoint scalars ---------------------------------------------------------------------------- */
 /* auto-reset on (default, DummyVecEnv semantics) or off (a bare RobotTaskEnv: finished envs keep their state and
  * keep stepping until the caller resets them, core.py:303-317). */

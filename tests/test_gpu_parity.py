@@ -542,3 +542,96 @@ def test_chain_layout_change_never_reuses_reset_stream_positions(ug):
         for a in ring:
             ref.step(a)
     assert torch.equal(ref.obs, env.obs) and torch.equal(ref.get_state("goal"), env.get_state("goal"))
+
+
+def _shipped_policy(ug, env_id, device):
+    from tests.closed_loop import SHORT
+    import os
+    w = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"policy_{SHORT[env_id]}.npz"))
+    return ug.mlp_policy({k: torch.as_tensor(w[k], device=device) for k in w.files if not k.startswith("published")})
+
+
+def test_device_rollout_matches_vecenv_transitions(ug):
+    """Rollout (policy -> urgym_step -> urgym_replay_write, all on the device) stores exactly the transitions an SB3-style
+    loop over SB3VecEnvAdapter would put into its replay buffer (train.py:39-60 through DummyVecEnv): obs, action, reward,
+    next_obs = terminal_observation for finished envs, done, TimeLimit.truncated."""
+    env_id, n, steps = "UR5DynReach-v1", 384, 45
+    env = ug.UR5VecEnv(env_id, n, seed=6)
+    env.reset()
+    policy = _shipped_policy(ug, env_id, env.device)
+    noisy = lambda o: torch.clamp(policy(o) + 0.6 * torch.sin(o["observation"][:, :6] * 37.0), -1, 1)   # exploration, deterministic
+    ring = ug.DeviceReplayRing(env, capacity=n * steps)
+    ro = ug.Rollout(env, noisy, ring)
+    ro.run(steps)
+    torch.cuda.synchronize()
+    assert int(ring.cursor.item()) == n * steps and len(ring) == n * steps
+    venv = ug.SB3VecEnvAdapter(env_id, n, seed=6)
+    obs = venv.reset()
+    seen_done = seen_timeout = 0
+    for t in range(steps):
+        od = {k: torch.as_tensor(v).cuda() for k, v in obs.items()}
+        a = noisy(od).cpu().numpy()
+        nobs, rew, dones, infos = venv.step(a)
+        rows = slice(t * n, (t + 1) * n)
+        assert np.array_equal(ring.obs[rows].cpu().numpy(), obs["observation"])
+        assert np.array_equal(ring.actions[rows].cpu().numpy(), a)
+        assert np.array_equal(ring.reward[rows].cpu().numpy(), rew)
+        assert np.array_equal(ring.done[rows].cpu().numpy().astype(bool), dones)
+        nxt = nobs["observation"].copy()
+        for i in np.nonzero(dones)[0]:
+            nxt[i] = infos[i]["terminal_observation"]["observation"]
+        assert np.array_equal(ring.next_obs[rows].cpu().numpy(), nxt)
+        to = np.array([infos[i]["TimeLimit.truncated"] for i in range(n)])
+        assert np.array_equal(ring.timeout[rows].cpu().numpy().astype(bool), to)
+        seen_done += int(dones.sum()); seen_timeout += int(to.sum())
+        obs = nobs
+    assert seen_done > 0
+    batch = ring.sample(256)
+    assert batch["observations"].shape == (256, 35) and batch["dones"].max() <= 1.0
+    venv.close()
+
+
+def test_device_rollout_graph_equals_eager_and_ring_wraps(ug):
+    env_id, n = "UR5StaReach-v1", 2048
+    envs = [ug.UR5VecEnv(env_id, n, seed=4) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    policy = _shipped_policy(ug, env_id, envs[0].device)
+    rings = [ug.DeviceReplayRing(e, capacity=n * 6) for e in envs]        # 6 steps of capacity: the ring wraps
+    eager, graphed = ug.Rollout(envs[0], policy, rings[0]), ug.Rollout(envs[1], policy, rings[1])
+    graphed.capture(4)            # (one eager warm-up step inside capture())
+    graphed.replay(3)
+    eager.run(1 + 4 * 3)
+    torch.cuda.synchronize()
+    for name in ("obs", "next_obs", "actions", "reward", "done", "timeout", "cursor"):
+        assert torch.equal(getattr(rings[0], name), getattr(rings[1], name)), name
+    assert int(rings[0].cursor.item()) == 13 * n and len(rings[0]) == 6 * n
+    assert torch.equal(envs[0].obs, envs[1].obs)
+
+
+def test_async_host_step_matches_sync(ug):
+    """urgym_step_host_async with two slots in flight == urgym_step_host, step for step"""
+    env_id, n = "UR5DynReach-v1", 300_000
+    a_env, b_env = ug.UR5VecEnv(env_id, n, seed=12), ug.UR5VecEnv(env_id, n, seed=12)
+    a_env.reset(); b_env.reset()
+    sync = a_env.alloc_host_buffers()
+    slots = [b_env.alloc_host_buffers() for _ in range(2)]
+    rng = np.random.default_rng(3)
+    acts = [torch.from_numpy(rng.uniform(-1, 1, (n, 6)).astype(np.float32)).pin_memory() for _ in range(7)]
+    expect = []
+    for a in acts:
+        a_env.step_host(a, sync)
+        expect.append({k: v.clone() for k, v in sync.items() if k != "actions"})
+    b_env.step_host_async(0, acts[0], slots[0])
+    for k in range(1, len(acts)):
+        b_env.step_host_async(k % 2, acts[k], slots[k % 2])      # enqueued before the previous step was waited for
+        b_env.host_wait((k - 1) % 2)
+        done = (expect[k - 1]["terminated"] | expect[k - 1]["truncated"]).bool()
+        for key in ("obs", "reward", "terminated", "truncated", "is_success"):
+            assert torch.equal(slots[(k - 1) % 2][key], expect[k - 1][key]), (k, key)
+        assert torch.equal(slots[(k - 1) % 2]["terminal_obs"][done], expect[k - 1]["terminal_obs"][done])
+    b_env.host_wait((len(acts) - 1) % 2)
+    assert torch.equal(slots[(len(acts) - 1) % 2]["obs"], expect[-1]["obs"])
+    with pytest.raises(ug.UrgymError):
+        b_env.step_host_async(0, acts[0], slots[0]); b_env.step_host_async(0, acts[1], slots[0])   # slot still in flight
+    b_env.host_wait(0)

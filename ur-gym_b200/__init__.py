@@ -9,5 +9,6 @@ from .envs import ENV_IDS, RobotTaskEnv, make, register_with_gymnasium  # noqa: 
 from .sharding import allreduce_stats, shard_range, summarize  # noqa: F401
 from .sb3_vec_env import SB3VecEnvAdapter  # noqa: F401
 from .vec_env import UR5VecEnv  # noqa: F401
+from .rollout import DeviceReplayRing, Rollout, mlp_policy  # noqa: F401
 
 register_with_gymnasium()

@@ -26,7 +26,7 @@ STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions",
 
 EXPORTS = ["urgym_step_range", "urgym_create", "urgym_destroy", "urgym_last_error", "urgym_obs_dim", "urgym_goal_dim", "urgym_num_envs",
            "urgym_step", "urgym_reset", "urgym_observe", "urgym_refresh", "urgym_get_state", "urgym_set_state",
-           "urgym_stats", "urgym_step_host", "urgym_reset_host", "urgym_step_host_async", "urgym_host_wait", "urgym_set_autoreset", "urgym_get_event",
+           "urgym_stats", "urgym_step_host", "urgym_reset_host", "urgym_step_host_async", "urgym_host_wait", "urgym_replay_write", "urgym_set_autoreset", "urgym_get_event",
            "urgym_set_event", "urgym_set_seed", "urgym_set_link_dist_mode", "urgym_sync_events", "urgym_launch_count", "urgym_profile_enable", "urgym_profile_read"]
 
 
@@ -62,6 +62,7 @@ def lib():
         L.urgym_reset_host.argtypes = [vp, vp, vp, vp, vp]
         L.urgym_step_host_async.argtypes = [vp, i32] + [vp] * 10
         L.urgym_host_wait.argtypes = [vp, i32]
+        L.urgym_replay_write.argtypes = [vp] + [vp] * 13 + [i64, vp, vp]
         L.urgym_set_autoreset.argtypes = [vp, i32]
         L.urgym_get_event.argtypes = [vp, ctypes.POINTER(u32)]
         L.urgym_set_event.argtypes = [vp, u32]

@@ -673,6 +673,70 @@ extern "C" int urgym_host_wait(urgym_env_t *h, int slot) {
     return URGYM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ replay ring
+// One transition per env and step into a device-resident ring (what SB3's DictReplayBuffer.add does on the host for
+// n_envs = 1: train.py:39-48 buffer_size=1e7; stable_baselines3 ReplayBuffer semantics): obs, action, reward, next_obs
+// (the TERMINAL observation for envs that finished, not the first observation of the next episode), done, and the
+// TimeLimit.truncated flag (handle_timeout_termination).  Row-major rings; the write cursor lives on the device so that
+// a captured graph of (policy, step, replay write) advances it on every replay.  HBM-bound copy kernel: one warp moves
+// whole rows with the lanes along the row.
+struct ReplayArgs {
+    int64_t n, capacity;
+    int D;
+    const float *obs, *act, *rew, *next_obs, *term_obs;
+    const uint8_t *terminated, *truncated;
+    float *r_obs, *r_next, *r_act, *r_rew;
+    uint8_t *r_done, *r_timeout;
+    unsigned long long *cursor;
+};
+__global__ void __launch_bounds__(256) urgym_replay_kernel(const ReplayArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long base = *A.cursor;
+    for (int64_t i = warp; i < A.n; i += nwarps) {
+        const int64_t slot = (int64_t)((base + (unsigned long long)i) % (unsigned long long)A.capacity);
+        const bool done = A.terminated[i] | A.truncated[i];
+        const float *nx = (done ? A.term_obs : A.next_obs) + i * A.D;
+        for (int c = lane; c < A.D; c += 32) {
+            A.r_obs[slot * A.D + c] = A.obs[i * A.D + c];
+            A.r_next[slot * A.D + c] = nx[c];
+        }
+        if (lane < 6) A.r_act[slot * 6 + lane] = A.act[i * 6 + lane];
+        if (lane == 6) A.r_rew[slot] = A.rew[i];
+        if (lane == 7) A.r_done[slot] = done ? 1 : 0;
+        if (lane == 8) A.r_timeout[slot] = (A.truncated[i] && !A.terminated[i]) ? 1 : 0;
+    }
+}
+static __global__ void urgym_replay_advance_kernel(unsigned long long *cursor, unsigned long long n) { *cursor += n; }
+
+extern "C" int urgym_replay_write(urgym_env_t *h, const float *obs, const float *actions, const float *reward,
+                                  const uint8_t *terminated, const uint8_t *truncated, const float *next_obs,
+                                  const float *terminal_obs, float *ring_obs, float *ring_next_obs, float *ring_actions,
+                                  float *ring_reward, uint8_t *ring_done, uint8_t *ring_timeout, int64_t capacity,
+                                  unsigned long long *cursor, void *stream) {
+    if (!h) return URGYM_EINVAL;
+    if (!obs || !actions || !reward || !terminated || !truncated || !next_obs || !terminal_obs || !ring_obs || !ring_next_obs ||
+        !ring_actions || !ring_reward || !ring_done || !ring_timeout || !cursor)
+        return fail(h, URGYM_EINVAL, "urgym_replay_write: NULL pointer%s", "");
+    if (capacity < h->n) return fail(h, URGYM_EINVAL, "urgym_replay_write: capacity must be at least the number of envs%s", "");
+    CK(cudaSetDevice(h->device));
+    ReplayArgs A;
+    A.n = h->n; A.capacity = capacity; A.D = obs_dim(h->task);
+    A.obs = obs; A.act = actions; A.rew = reward; A.next_obs = next_obs; A.term_obs = terminal_obs;
+    A.terminated = terminated; A.truncated = truncated;
+    A.r_obs = ring_obs; A.r_next = ring_next_obs; A.r_act = ring_actions; A.r_rew = ring_reward;
+    A.r_done = ring_done; A.r_timeout = ring_timeout; A.cursor = cursor;
+    const int64_t warps = (h->n + 3) / 4;                   // four rows per warp
+    const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+    urgym_replay_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(A);
+    CK(cudaGetLastError());
+    urgym_replay_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(cursor, (unsigned long long)h->n);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    return URGYM_OK;
+}
+
 extern "C" int urgym_reset_host(urgym_env_t *h, const uint8_t *mask, float *obs, float *achieved, float *desired) {
     if (!h) return URGYM_EINVAL;
     CK(cudaSetDevice(h->device));
