@@ -20,9 +20,8 @@ static bool g_init = false;
 static void init() {
     if (g_init) return;
     build_model_const(g_M);
-    g_hull.resize(UR5E_NUM_HULL_VERTS);
-    for (int i = 0; i < UR5E_NUM_HULL_VERTS; i++)
-        g_hull[i] = make_float4((float)UR5E_HULL_VERTS[3 * i], (float)UR5E_HULL_VERTS[3 * i + 1], (float)UR5E_HULL_VERTS[3 * i + 2], 0.0f);
+    g_hull.resize(URGYM_HULL_BLOB_F4);
+    build_hull_blob(g_hull.data());
     g_init = true;
 }
 

@@ -14,6 +14,10 @@ from tests._parity import obs_close, run_parity, sta_moving_scenarios
 
 pytestmark = pytest.mark.gpu
 TASKS = ["UR5OriReach-v1", "UR5ObsReach-v1", "UR5StaReach-v1", "UR5DynReach-v1"]
+# hull geometry: FP32 link poses differ from the oracle's FP64 poses by up to ~1.5e-6 m, and so do the GJK distances
+# built on them (pairs whose FP32 iteration does not converge are redone in FP64: urgym_device.cuh gjk_distance_refine).
+# The budget: link distances 5e-6 m; rewards additionally 100 (Obs weight) x 5 links x 2 distances x 2e-6 m.
+HULL_LD_TOL, HULL_REW_ATOL = 5e-6, 2e-3
 
 
 @pytest.fixture(scope="module")
@@ -46,7 +50,7 @@ def test_hull_rollout_parity(env_id, ug):
     from tests._gpu import GpuSim
     n, steps = 40, 40
     st = run_parity(GpuSim(env_id, oe.GEOM_HULL, n, seed=3, offset=77), env_id, oe.GEOM_HULL, n, steps, seed=3, offset=77,
-                    ld_tol=5e-5, rew_atol=1e-2)
+                    ld_tol=HULL_LD_TOL, rew_atol=HULL_REW_ATOL)
     assert st["steps"] > 0.85 * n * steps, st
 
 
@@ -468,7 +472,7 @@ def test_sta_moving_obstacle_injection(geom, ug):
 
     # (hull: a tilting cylinder brings its rims to the links more often than the static scenes do; FP32 GJK against a rim
     # converges sublinearly)
-    kw = dict(ld_tol=1e-4, rew_atol=1e-2) if geom == oe.GEOM_HULL else {}
+    kw = dict(ld_tol=HULL_LD_TOL, rew_atol=HULL_REW_ATOL) if geom == oe.GEOM_HULL else {}
     st = run_parity(GpuSim("UR5StaReach-v1", geom, n, seed=8, offset=40), "UR5StaReach-v1", geom, n, steps, seed=8, offset=40,
                     action_scale=0.6, after_reset=inject, **kw)
     assert st["steps"] > 0.8 * n * steps and st["resets"] > 0, st

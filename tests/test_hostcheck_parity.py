@@ -10,6 +10,10 @@ from tests._parity import run_parity, sta_moving_scenarios
 from oracle import oracle_env as oe
 
 TASKS = ["UR5OriReach-v1", "UR5ObsReach-v1", "UR5StaReach-v1", "UR5DynReach-v1"]
+# hull geometry: FP32 link poses differ from the oracle's FP64 poses by up to ~1.5e-6 m, and so do the GJK distances
+# built on them (pairs whose FP32 iteration does not converge are redone in FP64: urgym_device.cuh gjk_distance_refine).
+# The budget: link distances 5e-6 m; rewards additionally 100 (Obs weight) x 5 links x 2 distances x 2e-6 m.
+HULL_LD_TOL, HULL_REW_ATOL = 5e-6, 2e-3
 
 
 def test_philox_matches_oracle_and_known_answer():
@@ -53,7 +57,7 @@ def test_capsule_rollout_parity(env_id):
 def test_hull_rollout_parity(env_id):
     n, steps = 16, 40
     sim = HostCheckSim(env_id, oe.GEOM_HULL, n, seed=99, offset=1000)
-    st = run_parity(sim, env_id, oe.GEOM_HULL, n, steps, seed=99, offset=1000, ld_tol=5e-5, rew_atol=1e-2)
+    st = run_parity(sim, env_id, oe.GEOM_HULL, n, steps, seed=99, offset=1000, ld_tol=HULL_LD_TOL, rew_atol=HULL_REW_ATOL)
     assert st["steps"] > 0.9 * n * steps, st
 
 
@@ -67,7 +71,7 @@ def test_workbench_link_dist_mode_parity(env_id, geom):
     sim = HostCheckSim(env_id, geom, n, seed=21, offset=300, link_dist_mode=oe.LD_WORKBENCH)
     # hull geometry: FP32 GJK between a tessellated-cylinder hull and a box face parallel to it stalls 6e-5 short of the
     # optimum (upper arm above the track); this mode exists for the closed-loop check, a statistical comparison
-    kw = dict(ld_tol=1e-4, rew_atol=1e-2) if geom == oe.GEOM_HULL else {}
+    kw = dict(ld_tol=HULL_LD_TOL, rew_atol=HULL_REW_ATOL) if geom == oe.GEOM_HULL else {}
     st = run_parity(sim, env_id, geom, n, steps, seed=21, offset=300, link_dist_mode=oe.LD_WORKBENCH, **kw)
     assert st["steps"] > 0.85 * n * steps, st
 
@@ -88,7 +92,7 @@ def test_sta_moving_obstacle_injection(geom):
             e.task.set_goal_and_obstacle(sc[i].astype(np.float64))
 
     sim = HostCheckSim("UR5StaReach-v1", geom, n, seed=8, offset=40)
-    kw = dict(ld_tol=5e-5, rew_atol=1e-2) if geom == oe.GEOM_HULL else {}
+    kw = dict(ld_tol=HULL_LD_TOL, rew_atol=HULL_REW_ATOL) if geom == oe.GEOM_HULL else {}
     st = run_parity(sim, "UR5StaReach-v1", geom, n, steps, seed=8, offset=40, action_scale=0.6, after_reset=inject, **kw)
     assert st["steps"] > 0.8 * n * steps and (st["resets"] > 0 or geom == oe.GEOM_HULL), st
     moved = np.linalg.norm(sim.E[:, 12:15] - sim.E[:, 6:9], axis=1)

@@ -227,9 +227,8 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
             if ((e = k_prepare[geom][task](h->model, dummy, 0)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
         }
         if ((geom & 1) == URGYM_GEOM_HULL) {
-            static float4 hv[UR5E_NUM_HULL_VERTS];
-            for (int i = 0; i < UR5E_NUM_HULL_VERTS; i++)
-                hv[i] = make_float4((float)UR5E_HULL_VERTS[3 * i], (float)UR5E_HULL_VERTS[3 * i + 1], (float)UR5E_HULL_VERTS[3 * i + 2], 0.0f);
+            static float4 hv[URGYM_HULL_BLOB_F4];
+            build_hull_blob(hv);
             if ((e = cudaMalloc(&h->hull, sizeof(hv))) != cudaSuccess) { rc = URGYM_ENOMEM; break; }
             if ((e = cudaMemcpy(h->hull, hv, sizeof(hv), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = URGYM_ECUDA; break; }
         }

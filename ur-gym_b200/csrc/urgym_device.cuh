@@ -141,6 +141,8 @@ struct alignas(16) ModelConst {
     float fit_obst_h, fit_obst_ie;
     float box_top;              // highest top face of the table / track cores (z), for the height broad phase
     int hull_off[8];            // vertex ranges of links 0..6 inside the packed float4 vertex array
+    unsigned short hull_start[7][8];    // per link and octant of the (link-frame) direction: support vertex of the octant's
+                                        // diagonal, where the hill-climbing support function starts its first walk
     // margins of Bullet's GJK pair detector (distance = |core gap| - marginA - marginB)
     float hull_margin;          // URDF mesh links: 0.001
     float box_c[2][3], box_he[2][3], box_margin[2];    // 0 = table, 1 = track; core half extents (shrunk by the margin)
@@ -474,19 +476,48 @@ URGYM_HD void euler_obstacle(float u_sign, float u_roll, float u_pitch, float &r
 
 // ------------------------------------------------------------------------------------------------ convex cores
 // support points of the cores Bullet's GJK sees (btConvexShape::localGetSupportVertexWithoutMarginNonVirtual)
+// The hull "blob" every hull-geometry kernel stages in shared memory: float4 vertices of all links (link frame), then
+// the adjacency of the triangulated hulls (tools/make_hull_adjacency.py): uint16 offsets per vertex (+1), uint16 LOCAL
+// neighbour indices.  Sizes in ur5e_hull_adjacency.h / ur5e_model_data.h; layout fixed here.
+#define URGYM_HULL_NV 3793
+#define URGYM_HULL_NADJ 22674
+#define URGYM_HULL_OFF_U16 3800                     /* NV + 1 offsets, padded to a multiple of 8 */
+#define URGYM_HULL_ADJ_U16 22680                    /* padded to a multiple of 8 */
+#define URGYM_HULL_BLOB_F4 (URGYM_HULL_NV + (URGYM_HULL_OFF_U16 + URGYM_HULL_ADJ_U16) / 8)
+URGYM_HD const unsigned short *hull_adj_off(const float4 *blob) { return reinterpret_cast<const unsigned short *>(blob + URGYM_HULL_NV); }
+URGYM_HD const unsigned short *hull_adj(const float4 *blob) { return hull_adj_off(blob) + URGYM_HULL_OFF_U16; }
+
 struct HullW {                      // link hull: vertices in the link frame (shared memory), posed by T
     const float4 *v; int n; const Pose *T;
+    const unsigned short *aoff, *adj;       // adjacency of THIS link: aoff[k] .. aoff[k + 1] index adj (local neighbour ids)
+    const unsigned short *start;            // ModelConst::hull_start of this link
+    mutable int cur;                        // last support vertex: the next query starts its walk there (-1: none yet)
     URGYM_HD float3 center() const { return T->p; }
-    URGYM_HD float3 support(float3 d) const {
-        float3 l = rotT(T->R, d);
-        float best = -3.0e38f; int bi = 0;
-#pragma unroll 4
-        for (int i = 0; i < n; i++) {
-            float4 p = v[i];
-            float s = fmaf(p.x, l.x, fmaf(p.y, l.y, p.z * l.z));
-            if (s > best) { best = s; bi = i; }
+    // Support vertex by steepest ascent over the hull's edges: on a convex polytope a vertex with no better neighbour is
+    // the maximum.  Consecutive GJK directions are close, so after the first query the walk is one or two edges long
+    // (the exhaustive scan of round 1 looked at all 73..998 vertices of the link in every query).
+    URGYM_HD float3 support(float3 d) const { return hull_support(*this, d); }
+    static URGYM_OOL float3 hull_support(const HullW &H, float3 d) { return H.support_impl(d); }
+    URGYM_HD float3 support_impl(float3 d) const {
+        const float3 l = rotT(T->R, d);
+        int c = cur;
+        if (c < 0) c = start[(l.x > 0.0f ? 1 : 0) | (l.y > 0.0f ? 2 : 0) | (l.z > 0.0f ? 4 : 0)];   // first query of this hull
+        float4 p = v[c];
+        float best = fmaf(p.x, l.x, fmaf(p.y, l.y, p.z * l.z));
+        for (int it = 0; it < n; it++) {
+            int nxt = -1;
+            const int e1 = aoff[c + 1];
+            for (int e = aoff[c]; e < e1; e++) {
+                const int k = adj[e];
+                const float4 q = v[k];
+                const float s = fmaf(q.x, l.x, fmaf(q.y, l.y, q.z * l.z));
+                if (s > best) { best = s; nxt = k; }
+            }
+            if (nxt < 0) break;
+            c = nxt;
         }
-        float4 p = v[bi];
+        cur = c;
+        p = v[c];
         return rot(T->R, f3(p.x, p.y, p.z)) + T->p;
     }
 };
@@ -529,7 +560,7 @@ struct BoxO {                       // oriented cube core (Sta/Dyn target)
 // equations; when it falls outside (or the triangle is degenerate) the best of the three edge projections.
 // Written for FP32 robustness rather than minimum flops: region classification by products of large dot products
 // (the classic formulation) stalls GJK when the simplex is small next to its distance from the origin.
-URGYM_HD void closest_tri(float3 a, float3 b, float3 c, float &la, float &lb, float &lc) {
+static URGYM_OOL void closest_tri(float3 a, float3 b, float3 c, float &la, float &lb, float &lc) {
     float3 ab = b - a, ac = c - a, bc = c - b;
     float s = -dot(a, ab), t = -dot(a, ac);
     float E = dot(ab, ab), F = dot(ab, ac), G = dot(ac, ac);
@@ -554,7 +585,7 @@ URGYM_HD void closest_tri(float3 a, float3 b, float3 c, float &la, float &lb, fl
 }
 
 // Reduce the simplex to the sub-simplex supporting the point closest to the origin (v).  true = origin enclosed.
-URGYM_HD bool closest_simplex(float3 (&W)[4], int &n, float3 &v) {
+static URGYM_OOL bool closest_simplex(float3 (&W)[4], int &n, float3 &v) {
     float l[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (n == 1) {
         l[0] = 1.0f;
@@ -627,7 +658,7 @@ URGYM_HD bool closest_simplex(float3 (&W)[4], int &n, float3 &v) {
 
 // distance between the cores of A and B (0 and deep=true when they intersect)
 template <class SA, class SB>
-URGYM_HD float gjk_distance(const SA &A, const SB &B, bool &deep, float3 *v_out = nullptr) {
+URGYM_HD float gjk_distance(const SA &A, const SB &B, bool &deep, float3 *v_out = nullptr, float *lb_out = nullptr) {
     float3 W[4];
     int n = 1;
     float3 d = A.center() - B.center();
@@ -660,7 +691,128 @@ URGYM_HD float gjk_distance(const SA &A, const SB &B, bool &deep, float3 *v_out 
         v = vn; vv = vvn;
     }
     if (v_out) *v_out = v;          // closest vector (from B to A) of the last iterate
+    if (lb_out) *lb_out = lb;       // proven lower bound of the distance
     return sqrtf(vv);
+}
+
+// ------------------------------------------------------------------------------------------------ FP64 refinement
+// The FP32 iteration above ends within ~1e-6 m of the FP64 answer in all but a few pairs per ten thousand: contacts with
+// a cylinder RIM (GJK converges only sublinearly on a curved edge: 48 iterations are not enough) and faces that are
+// nearly parallel (the FP32 simplex update stalls).  Those are recognisable -- the iteration ends with a gap between its
+// proven lower bound and its distance -- and are redone here: the same algorithm with the simplex arithmetic in double
+// and up to 256 iterations.  Rare, out of line.
+struct D3 { double x, y, z; };
+URGYM_HD D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+URGYM_HD D3 d3(float3 a) { return d3((double)a.x, (double)a.y, (double)a.z); }
+URGYM_HD D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+URGYM_HD D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+URGYM_HD D3 operator*(double s, D3 a) { return d3(s * a.x, s * a.y, s * a.z); }
+URGYM_HD double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+URGYM_HD D3 dcross(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+URGYM_HD double dclamp(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+static URGYM_OOL void closest_tri_d(D3 a, D3 b, D3 c, double &la, double &lb, double &lc) {
+    D3 ab = b - a, ac = c - a, bc = c - b;
+    double s = -ddot(a, ab), t = -ddot(a, ac);
+    double E = ddot(ab, ab), F = ddot(ab, ac), G = ddot(ac, ac);
+    double det = E * G - F * F;
+    if (det > 1e-20 * E * G) {
+        double u = s * G - t * F, v = t * E - s * F;
+        if (u >= 0.0 && v >= 0.0 && u + v <= det) {
+            double inv = 1.0 / det;
+            lb = u * inv; lc = v * inv; la = 1.0 - lb - lc;
+            return;
+        }
+    }
+    double t1 = E > 0.0 ? dclamp(s / E, 0.0, 1.0) : 0.0;
+    double t2 = G > 0.0 ? dclamp(t / G, 0.0, 1.0) : 0.0;
+    double H = ddot(bc, bc);
+    double t3 = H > 0.0 ? dclamp(-ddot(b, bc) / H, 0.0, 1.0) : 0.0;
+    D3 x1 = a + t1 * ab, x2 = a + t2 * ac, x3 = b + t3 * bc;
+    double d1 = ddot(x1, x1), d2 = ddot(x2, x2), d3_ = ddot(x3, x3);
+    if (d1 <= d2 && d1 <= d3_) { la = 1.0 - t1; lb = t1; lc = 0.0; }
+    else if (d2 <= d3_) { la = 1.0 - t2; lb = 0.0; lc = t2; }
+    else { la = 0.0; lb = 1.0 - t3; lc = t3; }
+}
+static URGYM_OOL bool closest_simplex_d(D3 (&W)[4], int &n, D3 &v) {
+    double l[4] = {0.0, 0.0, 0.0, 0.0};
+    if (n == 1) {
+        l[0] = 1.0;
+    } else if (n == 2) {
+        D3 ab = W[1] - W[0];
+        double den = ddot(ab, ab), t = den > 0.0 ? -ddot(W[0], ab) / den : 0.0;
+        t = dclamp(t, 0.0, 1.0);
+        l[0] = 1.0 - t; l[1] = t;
+    } else if (n == 3) {
+        closest_tri_d(W[0], W[1], W[2], l[0], l[1], l[2]);
+    } else {
+        D3 ad = W[0] - W[3], bd = W[1] - W[3], cd = W[2] - W[3], od = d3(-W[3].x, -W[3].y, -W[3].z);
+        double det = ddot(ad, dcross(bd, cd));
+        double m1 = ddot(ad, ad), m2 = ddot(bd, bd), m3 = ddot(cd, cd);
+        double L2 = m1 > m2 ? (m1 > m3 ? m1 : m3) : (m2 > m3 ? m2 : m3);
+        bool flat = det * det <= 1e-24 * L2 * L2 * L2;
+        double la = ddot(od, dcross(bd, cd)), lb = ddot(ad, dcross(od, cd)), lc = ddot(ad, dcross(bd, od));
+        if (det < 0.0) { la = -la; lb = -lb; lc = -lc; det = -det; }
+        double ld = det - la - lb - lc;
+        if (!flat && la > 0.0 && lb > 0.0 && lc > 0.0 && ld > 0.0) return true;
+        double best = 1e300, a, b, c;
+        if (flat || ld <= 0.0) {
+            closest_tri_d(W[0], W[1], W[2], a, b, c);
+            D3 p = a * W[0] + b * W[1] + c * W[2]; double dd = ddot(p, p);
+            if (dd < best) { best = dd; l[0] = a; l[1] = b; l[2] = c; l[3] = 0; }
+        }
+        if (flat || lb <= 0.0) {
+            closest_tri_d(W[0], W[2], W[3], a, b, c);
+            D3 p = a * W[0] + b * W[2] + c * W[3]; double dd = ddot(p, p);
+            if (dd < best) { best = dd; l[0] = a; l[1] = 0; l[2] = b; l[3] = c; }
+        }
+        if (flat || lc <= 0.0) {
+            closest_tri_d(W[0], W[3], W[1], a, b, c);
+            D3 p = a * W[0] + b * W[3] + c * W[1]; double dd = ddot(p, p);
+            if (dd < best) { best = dd; l[0] = a; l[1] = c; l[2] = 0; l[3] = b; }
+        }
+        if (flat || la <= 0.0) {
+            closest_tri_d(W[1], W[3], W[2], a, b, c);
+            D3 p = a * W[1] + b * W[3] + c * W[2]; double dd = ddot(p, p);
+            if (dd < best) { best = dd; l[0] = 0; l[1] = a; l[2] = c; l[3] = b; }
+        }
+    }
+    D3 nv = d3(0, 0, 0), T[4];
+    int m = 0;
+    for (int i = 0; i < 4; i++) {
+        if (i < n && l[i] > 0.0) { nv = nv + l[i] * W[i]; T[m] = W[i]; m++; }
+    }
+    for (int i = 0; i < m; i++) W[i] = T[i];
+    n = m; v = nv;
+    return false;
+}
+#define URGYM_GJK_REFINE_ITER 256
+#define URGYM_GJK_REFINE_GAP 2.0e-6f      /* FP32 result accepted when its distance is proven to this (lower bound known) */
+template <class SA, class SB>
+static URGYM_OOL float gjk_distance_refine(const SA &A, const SB &B, float3 v0) {
+    D3 W[4];
+    int n = 1;
+    float3 vf = v0;
+    if (dot(vf, vf) < 1e-12f) vf = f3(1, 0, 0);
+    D3 v = d3(A.support(-vf)) - d3(B.support(vf));
+    W[0] = v;
+    double vv = ddot(v, v);
+    for (int it = 0; it < URGYM_GJK_REFINE_ITER; it++) {
+        if (vv < 1e-24) return 0.0f;
+        const float3 dir = f3((float)v.x, (float)v.y, (float)v.z);
+        D3 w = d3(A.support(-dir)) - d3(B.support(dir));
+        double delta = ddot(v, w);
+        if (vv - delta <= 1e-9 * vv) break;
+        bool dup = false;
+        for (int i = 0; i < n; i++) { D3 e = w - W[i]; dup = dup || (ddot(e, e) <= 1e-24); }
+        if (dup) break;
+        W[n] = w; n++;
+        D3 vn;
+        if (closest_simplex_d(W, n, vn)) return 0.0f;
+        double vvn = ddot(vn, vn);
+        if (vvn >= vv) break;
+        v = vn; vv = vvn;
+    }
+    return (float)sqrt(vv);
 }
 
 // ------------------------------------------------------------------------------------------------ closed forms

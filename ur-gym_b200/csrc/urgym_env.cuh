@@ -337,7 +337,7 @@ template <> struct LinkShape<GEOM_CAPSULE> {
 template <> struct LinkShape<GEOM_HULL> {
     Pose T;
     LinkShape<GEOM_CAPSULE> cap;
-    const float4 *hv;       // packed hull vertices (shared memory on the device)
+    const float4 *hv;       // the hull blob: packed vertices + adjacency (shared memory on the device)
     URGYM_HD void set(const ModelConst &M, int l, const Pose &P, const float4 *verts) { T = P; hv = verts; cap.set(M, l, P, verts); }
     URGYM_HD void set_neutral(const ModelConst &M, int l, const float4 *verts) {
         hv = verts;
@@ -348,6 +348,7 @@ template <> struct LinkShape<GEOM_HULL> {
     }
     URGYM_HD HullW hull(const ModelConst &M, int l) const {
         HullW H; H.v = hv + M.hull_off[l]; H.n = M.hull_off[l + 1] - M.hull_off[l]; H.T = &T;
+        H.aoff = hull_adj_off(hv) + M.hull_off[l]; H.adj = hull_adj(hv); H.start = M.hull_start[l]; H.cur = -1;
         return H;
     }
     URGYM_HD float obstacle_dist(const ModelConst &M, int l, const ObstW &O) const {
@@ -357,33 +358,47 @@ template <> struct LinkShape<GEOM_HULL> {
         // wall and distance(hull, cylinder) = distance(hull, axis segment) - radius exactly.
         bool deep;
         float3 v;
+        float lb;
         SegW S; S.a = O.c - M.obst_h * O.u; S.b = O.c + M.obst_h * O.u;
-        float ds = gjk_distance(hull(M, l), S, deep, &v);
-        if (!deep && ds > M.obst_r && fabsf(dot(v, O.u)) <= 1e-5f * ds)
+        const HullW H = hull(M, l);
+        float ds = gjk_distance(H, S, deep, &v, &lb);
+        if (!deep && ds > M.obst_r && fabsf(dot(v, O.u)) <= 1e-5f * ds) {
+            if (ds - lb > URGYM_GJK_REFINE_GAP) ds = gjk_distance_refine(H, S, v);
             return ds - M.obst_r - M.hull_margin - M.obst_margin;
+        }
         CylW C; C.c = O.c; C.u = O.u; C.r = M.obst_r; C.h = M.obst_h;      // end caps / rims / penetration
-        float d = gjk_distance(hull(M, l), C, deep);
+        float d = gjk_distance(H, C, deep, &v, &lb);
+        if (!deep && d - lb > URGYM_GJK_REFINE_GAP) d = gjk_distance_refine(H, C, v);
         return d - M.hull_margin - M.obst_margin;
     }
     URGYM_HD float box_dist(const ModelConst &M, int l, int box) const {      // link-distance mode "workbench"
         BoxA B; B.c = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
         B.he = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
-        bool deep;
-        return gjk_distance(hull(M, l), B, deep) - M.hull_margin - M.box_margin[box];
+        bool deep; float3 v; float lb;
+        const HullW H = hull(M, l);
+        float d = gjk_distance(H, B, deep, &v, &lb);
+        if (!deep && d - lb > URGYM_GJK_REFINE_GAP) d = gjk_distance_refine(H, B, v);
+        return d - M.hull_margin - M.box_margin[box];
     }
     URGYM_HD bool box_hit(const ModelConst &M, int l, int box) const {
         if (!cap.box_hit(M, l, box)) return false;
         BoxA B; B.c = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
         B.he = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
-        bool deep;
-        float d = gjk_distance(hull(M, l), B, deep);
-        return d - M.hull_margin - M.box_margin[box] <= URGYM_COLLISION_MARGIN;
+        bool deep; float3 v; float lb;
+        const HullW H = hull(M, l);
+        float d = gjk_distance(H, B, deep, &v, &lb);
+        const float thr = URGYM_COLLISION_MARGIN + M.hull_margin + M.box_margin[box];
+        if (!deep && d - lb > URGYM_GJK_REFINE_GAP && fabsf(d - thr) < 1e-3f) d = gjk_distance_refine(H, B, v);   // undecided near the threshold
+        return d <= thr;
     }
     URGYM_HD bool link_hit(const ModelConst &M, int l, int l2, const LinkShape &o) const {
         if (!cap.link_hit(M, l, l2, o.cap)) return false;
-        bool deep;
-        float d = gjk_distance(hull(M, l), o.hull(M, l2), deep);
-        return d - 2.0f * M.hull_margin <= URGYM_COLLISION_MARGIN;
+        bool deep; float3 v; float lb;
+        const HullW H1 = hull(M, l), H2 = o.hull(M, l2);
+        float d = gjk_distance(H1, H2, deep, &v, &lb);
+        const float thr = URGYM_COLLISION_MARGIN + 2.0f * M.hull_margin;
+        if (!deep && d - lb > URGYM_GJK_REFINE_GAP && fabsf(d - thr) < 1e-3f) d = gjk_distance_refine(H1, H2, v);
+        return d <= thr;
     }
 };
 

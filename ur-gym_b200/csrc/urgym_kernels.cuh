@@ -159,11 +159,24 @@ struct StepArgs {
 
 __device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// stage the hull vertices in shared memory (hull mode only): every lane of a warp walks the same vertex list, so
-// the support-function loop reads shared memory as a broadcast
+#ifndef URGYM_AUTORESET_BLOCK
+#define URGYM_AUTORESET_BLOCK 32    /* one warp per block: the warps finish at very different times (rejection loops) */
+#endif
+#ifndef URGYM_HULL_BLOCK
+#define URGYM_HULL_BLOCK 512
+#endif
+// Block sizes.  Capsule geometry: 128-thread blocks, six resident per SM.  Hull geometry: every block stages the 111 KB
+// hull blob (vertices + adjacency, urgym_device.cuh) in shared memory, so one big block per SM shares one copy.
+template <int GEOM> struct Blk {
+    static constexpr bool HULL = URGYM_BASE(GEOM) == GEOM_HULL;
+    static constexpr int STEP = HULL ? URGYM_HULL_BLOCK : URGYM_BLOCK;
+    static constexpr int STEP_MINBLOCKS = HULL ? 1 : URGYM_STEP_MINBLOCKS;
+    static constexpr int AUTORESET = HULL ? 256 : URGYM_AUTORESET_BLOCK;
+};
+// stage the hull blob in shared memory (hull mode only): the hill-climbing support function gathers from it per lane
 template <int GEOM> __device__ __forceinline__ const float4 *stage_hull(const float4 *g, float4 *s) {
     if (URGYM_BASE(GEOM) != GEOM_HULL) return nullptr;
-    for (int i = threadIdx.x; i < UR5E_NUM_HULL_VERTS; i += blockDim.x) s[i] = g[i];
+    for (int i = threadIdx.x; i < URGYM_HULL_BLOB_F4; i += blockDim.x) s[i] = g[i];
     return s;
 }
 // per-warp tile: 32 observation rows; the capsule pass's scratch column block [41][32] overlays it
@@ -171,8 +184,8 @@ template <int TASK> struct TileFloats {
     static constexpr int value = Traits<TASK>::OBS > URGYM_SCRATCH_FLOATS ? Traits<TASK>::OBS : URGYM_SCRATCH_FLOATS;
 };
 template <int TASK, int GEOM> constexpr size_t step_smem_bytes() {
-    return (size_t)URGYM_BLOCK * TileFloats<TASK>::value * sizeof(float) +
-           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
+    return (size_t)Blk<GEOM>::STEP * TileFloats<TASK>::value * sizeof(float) +
+           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)URGYM_HULL_BLOB_F4 * sizeof(float4) : 0);
 }
 __device__ __forceinline__ void stat_add(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }   // RED.E.ADD.64 (result unused)
 
@@ -182,9 +195,9 @@ __device__ __forceinline__ void stat_add(unsigned long long *p, unsigned long lo
 // Finished envs are NOT reset here: the step only raises their terminated / truncated flags, and the auto-reset
 // kernel that follows in the stream handles them in dense form.
 template <int TASK, int GEOM>
-__global__ void __launch_bounds__(URGYM_BLOCK, URGYM_STEP_MINBLOCKS) urgym_step_kernel(const __grid_constant__ ModelConst c_model, const StepArgs A) {
+__global__ void __launch_bounds__(Blk<GEOM>::STEP, Blk<GEOM>::STEP_MINBLOCKS) urgym_step_kernel(const __grid_constant__ ModelConst c_model, const StepArgs A) {
     typedef Traits<TASK> TT;
-    constexpr int D = TT::OBS, G = TT::GOAL, B = URGYM_BLOCK, W = 32;
+    constexpr int D = TT::OBS, G = TT::GOAL, B = Blk<GEOM>::STEP, W = 32;
     constexpr int TF = TileFloats<TASK>::value;
     extern __shared__ float4 smem4[];
     float *s_tiles = reinterpret_cast<float *>(smem4);        // [warps][32 * TF]: obs tile [32][D]
@@ -312,9 +325,6 @@ struct AuxArgs {
     unsigned *qcount;               // [0] entries, [1] block tickets of the auto-reset kernel
 };
 
-#ifndef URGYM_AUTORESET_BLOCK
-#define URGYM_AUTORESET_BLOCK 32    /* one warp per block: the warps finish at very different times (rejection loops) */
-#endif
 #ifndef URGYM_RESET_GROUP
 #define URGYM_RESET_GROUP 256       /* envs scanned by one warp of the reset kernel: ~11 finished envs at a 4 % done
                                        rate (measured on B200, Dyn 1 Mi envs: 128 -> 0.205, 256 -> 0.199, 512 -> 0.215 ms per step) */
@@ -505,9 +515,9 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_reset_kernel(const __grid_c
 // lanes are dense here: every warp takes 32 queue entries at a time.  The last block to finish empties the queue counter
 // for the next step.
 template <int TASK, int GEOM>
-__global__ void __launch_bounds__(URGYM_AUTORESET_BLOCK) urgym_autoreset_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
+__global__ void __launch_bounds__(Blk<GEOM>::AUTORESET) urgym_autoreset_kernel(const __grid_constant__ ModelConst c_model, const AuxArgs A) {
     typedef Traits<TASK> TT;
-    constexpr int D = TT::OBS, W = 32, NW = URGYM_AUTORESET_BLOCK / 32;
+    constexpr int D = TT::OBS, W = 32, NW = Blk<GEOM>::AUTORESET / 32;
     extern __shared__ float4 smem4[];
     float *s_rows_all = reinterpret_cast<float *>(smem4);                    // [NW][32][D] new observation rows
     int *s_list_all = reinterpret_cast<int *>(s_rows_all + NW * W * D);      // [NW][32]
@@ -542,12 +552,12 @@ __global__ void __launch_bounds__(URGYM_AUTORESET_BLOCK) urgym_autoreset_kernel(
     }
 }
 template <int TASK, int GEOM> constexpr size_t autoreset_smem_bytes() {
-    return (size_t)URGYM_AUTORESET_BLOCK * Traits<TASK>::OBS * sizeof(float) + 2 * URGYM_AUTORESET_BLOCK * sizeof(int) +
-           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
+    return (size_t)Blk<GEOM>::AUTORESET * Traits<TASK>::OBS * sizeof(float) + 2 * Blk<GEOM>::AUTORESET * sizeof(int) +
+           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)URGYM_HULL_BLOB_F4 * sizeof(float4) : 0);
 }
 template <int TASK, int GEOM> constexpr size_t reset_smem_bytes() {
     return (size_t)URGYM_BLOCK * Traits<TASK>::OBS * sizeof(float) + 2 * (URGYM_BLOCK / 32) * URGYM_RESET_GROUP * sizeof(int) +
-           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0);
+           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)URGYM_HULL_BLOB_F4 * sizeof(float4) : 0);
 }
 
 // every chain's reset-event counter := max over the chains + add.  add = 1: a reset event of its own (explicit reset,
@@ -616,7 +626,8 @@ __global__ void __launch_bounds__(URGYM_BLOCK) urgym_refresh_kernel(const __grid
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + URGYM_BLOCK - 1) / URGYM_BLOCK); }
 
 template <int TASK, int GEOM> cudaError_t launch_step(const ModelConst &M, const StepArgs &A, cudaStream_t s) {
-    urgym_step_kernel<TASK, GEOM><<<grid_for(A.n), URGYM_BLOCK, step_smem_bytes<TASK, GEOM>(), s>>>(M, A);
+    constexpr int B = Blk<GEOM>::STEP;
+    urgym_step_kernel<TASK, GEOM><<<(unsigned)((A.n + B - 1) / B), B, step_smem_bytes<TASK, GEOM>(), s>>>(M, A);
     return cudaGetLastError();
 }
 template <int TASK, int GEOM> cudaError_t launch_reset(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
@@ -626,14 +637,15 @@ template <int TASK, int GEOM> cudaError_t launch_reset(const ModelConst &M, cons
 }
 template <int TASK, int GEOM> cudaError_t launch_autoreset(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
     // enough warps for ~1/8 of the envs finishing in one step; beyond that the warps loop
-    const int64_t blocks = (A.n + 8 * URGYM_AUTORESET_BLOCK - 1) / (8 * URGYM_AUTORESET_BLOCK);
+    constexpr int AB = Blk<GEOM>::AUTORESET;
+    const int64_t blocks = (A.n + 8 * AB - 1) / (8 * AB);
     // Highest launch priority: the kernel is short, latency-bound and sits on the critical path of its chain
     // (step -> auto-reset -> next step), so its blocks should not queue behind the thousands of step-kernel blocks that
     // other chains have in flight.
     static int prio_hi = 1;
     if (prio_hi == 1) { int lo = 0; if (cudaDeviceGetStreamPriorityRange(&lo, &prio_hi) != cudaSuccess) prio_hi = 0; }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(URGYM_AUTORESET_BLOCK);
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(AB);
     cfg.dynamicSmemBytes = autoreset_smem_bytes<TASK, GEOM>(); cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributePriority; attr[0].val.priority = prio_hi;
@@ -641,7 +653,7 @@ template <int TASK, int GEOM> cudaError_t launch_autoreset(const ModelConst &M, 
     return cudaLaunchKernelEx(&cfg, urgym_autoreset_kernel<TASK, GEOM>, M, A);
 }
 template <int TASK, int GEOM> cudaError_t launch_refresh(const ModelConst &M, const AuxArgs &A, cudaStream_t s) {
-    const size_t smem = URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
+    const size_t smem = URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)URGYM_HULL_BLOB_F4 * sizeof(float4) : 0;
     urgym_refresh_kernel<TASK, GEOM><<<grid_for(A.n), URGYM_BLOCK, smem, s>>>(M, A);
     return cudaGetLastError();
 }
@@ -654,7 +666,7 @@ template <int TASK, int GEOM> cudaError_t prepare_kernels(const ModelConst &, co
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(urgym_autoreset_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)autoreset_smem_bytes<TASK, GEOM>());
     if (e != cudaSuccess) return e;
-    const size_t smem = URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)UR5E_NUM_HULL_VERTS * sizeof(float4) : 0;
+    const size_t smem = URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)URGYM_HULL_BLOB_F4 * sizeof(float4) : 0;
     if (smem) e = cudaFuncSetAttribute(urgym_refresh_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     return e;
 }

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "ur5e_model_data.h"
+#include "ur5e_hull_adjacency.h"
 #include "urgym_capsule_fit.h"
 #include "urgym_device.cuh"
 
@@ -28,6 +29,17 @@ static void host_fk(const double q[6], double pos[7][3], double R[7][9]) {
             R[j + 1][3 * r + 2] = A[3 * r + 2];
         }
     }
+}
+
+// the hull blob of urgym_device.cuh: vertices, adjacency offsets, adjacency (out: URGYM_HULL_BLOB_F4 float4)
+static void build_hull_blob(float4 *out) {
+    static_assert(UR5E_NUM_HULL_VERTS == URGYM_HULL_NV && UR5E_NUM_HULL_ADJ == URGYM_HULL_NADJ, "regenerate the hull tables");
+    memset(out, 0, sizeof(float4) * URGYM_HULL_BLOB_F4);
+    for (int i = 0; i < URGYM_HULL_NV; i++)
+        out[i] = make_float4((float)UR5E_HULL_VERTS[3 * i], (float)UR5E_HULL_VERTS[3 * i + 1], (float)UR5E_HULL_VERTS[3 * i + 2], 0.0f);
+    unsigned short *off = reinterpret_cast<unsigned short *>(out + URGYM_HULL_NV), *adj = off + URGYM_HULL_OFF_U16;
+    for (int i = 0; i <= URGYM_HULL_NV; i++) off[i] = UR5E_HULL_ADJ_OFF[i];
+    for (int i = 0; i < URGYM_HULL_NADJ; i++) adj[i] = UR5E_HULL_ADJ[i];
 }
 
 static void build_model_const(ModelConst &M) {
@@ -57,6 +69,16 @@ static void build_model_const(ModelConst &M) {
         M.cap_ia[l] = (float)(1.0 / hl);
     }
     for (int l = 0; l < 8; l++) M.hull_off[l] = UR5E_HULL_OFFSET[l];
+    for (int l = 0; l < 7; l++)
+        for (int o = 0; o < 8; o++) {
+            const double dx = (o & 1) ? 1.0 : -1.0, dy = (o & 2) ? 1.0 : -1.0, dz = (o & 4) ? 1.0 : -1.0;
+            int best = 0; double bv = -1e300;
+            for (int i = UR5E_HULL_OFFSET[l]; i < UR5E_HULL_OFFSET[l + 1]; i++) {
+                const double v = UR5E_HULL_VERTS[3 * i] * dx + UR5E_HULL_VERTS[3 * i + 1] * dy + UR5E_HULL_VERTS[3 * i + 2] * dz;
+                if (v > bv) { bv = v; best = i - UR5E_HULL_OFFSET[l]; }
+            }
+            M.hull_start[l][o] = (unsigned short)best;
+        }
     M.hull_margin = (float)hull_margin;
     const double pm = 0.001;                                // createCollisionShape primitives: margin 0.001, core shrunk
     // create_table(1.1, 1.8, 0.92, x_offset=0.5, z_offset=-0.12)   reach.py:169; pyb_setup.py:802-811
