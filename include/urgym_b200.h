@@ -37,7 +37,10 @@ enum { URGYM_TASK_ORI = 0,   /* UR5OriReach-v1  ReachOri  reach.py:141-236  obs 
 
 /* link geometry used by getClosestPoints stand-ins (pyb_setup.py:382-456) */
 enum { URGYM_GEOM_HULL = 0,     /* the reference's convex-hull links + cylinder/box scene, GJK distances */
-       URGYM_GEOM_CAPSULE = 1 };/* bounding capsules for links, capsule obstacle: closed-form distances (approximate) */
+       URGYM_GEOM_CAPSULE = 1 };/* one segment per link and for the obstacle, closed-form distances minus per-pair margins
+                                   CALIBRATED against the hull geometry (ur-gym_b200/csrc/urgym_capsule_fit.h) -- an
+                                   approximation, not a bound: on the hull path's own steady state the two collision
+                                   flags disagree in both directions (rates: profiles/disagreement_r02.json) */
 
 /* what `link_dist` (observation columns, reward term) measures: PyBullet.get_link_distances, pyb_setup.py:439-456 */
 enum { URGYM_LD_OBSTACLE = 0,   /* links 2..6 vs the obstacle: the code the reference ships (default)                  */
