@@ -152,7 +152,7 @@ void hc_ee_pose(int64_t n, const float *q, float *ee) {
 void hc_shift_box_z(int box, float dz) {
     init();
     g_M.box_c[box][2] += dz;
-    for (int l = 0; l < 7; l++) g_M.box_lim[l][box][0] += dz;
+    g_M.box_k[box][0] += dz;
 }
 // experiments: obstacle cylinder core radius / half height / margin
 void hc_set_obstacle(float r, float h, float margin) {

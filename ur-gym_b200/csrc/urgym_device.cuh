@@ -117,9 +117,10 @@ URGYM_HD float fdiv(float a, float b) {               // division where 2 ulp ar
 
 // ------------------------------------------------------------------------------------------------ constants
 struct alignas(16) ModelConst {
-    // table / track limits per (link, box), precomputed for the branch-free test of robot_pass_capsule:
-    //   [0] zthr = top + reach   [1] cx  [2] cy  [3] hx | [4] hy  [5] xlo = cx - hx - reach  [6] xhi  [7] ylo | [8] yhi
-    float box_lim[7][2][12];
+    // table / track constants of the branch-free test of box_tests (urgym_env.cuh); both boxes are centred on y = 0:
+    //   [0] top z  [1] cx  [2] hx  [3] hy | [4] cx - hx  [5] cx + hx  [6] -hy  [7] hy
+    float box_k[2][8];
+    float box_reach[8];         // per link: collision margin + fit_box[l] + box margin (the same for both boxes)
     // upper arm (link 2) vs table / track: constants of the separating-axis filter of robot_pass_capsule:
     //   [0] cx  [1] cz  [2] hx  [3] hz  [4] reach = margin + fit_box[2] + box margin
     float sat2[2][8];

@@ -476,11 +476,63 @@ static URGYM_OOL void workbench_link_dist(const ModelConst &M, float *cap, int c
         d = fminf(d, fminf(L.box_dist(M, l, 0), L.box_dist(M, l, 1)));
     }
 }
+// Table and track (pyb_setup.py:408-417) for ONE link with its end points in registers, branch-free for the common
+// cases.  With L the lower end point of the segment and dz = L.z - (top face of the box core): dz > reach means the whole
+// segment is farther than `reach` above the box, no hit; otherwise, if L lies over the box's footprint, dist(segment,
+// box) <= dist(L, box) = max(dz, 0) <= reach, a hit.  Only a low segment whose lower end is beside the footprint (table
+// edges, most track cases) needs the exact segment-box distance; those (link, box) pairs are collected in `slow`.
+// l is a compile-time value at every call site (the unrolled chain walk), so the per-(link, box) limits are immediate
+// constant-bank operands: done in a rolled loop over the links they cost one LDC each, a third of that loop's 340
+// instructions per warp.
+URGYM_HD void box_tests(const ModelConst &M, int l, float3 a, float3 b, bool &hit, unsigned &slow) {
+    const bool a_low = a.z <= b.z;
+    const float Lx = a_low ? a.x : b.x, Ly = a_low ? a.y : b.y, zmin = fminf(a.z, b.z);
+    const float minx = fminf(a.x, b.x), maxx = fmaxf(a.x, b.x), miny = fminf(a.y, b.y), maxy = fmaxf(a.y, b.y);
+    // Upper arm only: in steady state three quarters of the `slow` cases are the upper arm hanging down beside the track
+    // or behind the table, and 87 % of those are no hits.  The axis n = d x e_y (perpendicular to the segment and to the
+    // boxes' long edges) separates every one of them: the segment projects to a point, the box to |n_x| hx + |n_z| hz,
+    // and a gap beyond `reach` is a proven miss.
+    bool apart[2] = {false, false};
+    if (l == 2) {
+        const float dx = b.x - a.x, dz = b.z - a.z, mx = 0.5f * (a.x + b.x), mz = 0.5f * (a.z + b.z);
+        const float nn = sqrtf(fmaf(dx, dx, dz * dz));
+#pragma unroll
+        for (int box = 0; box < 2; box++) {
+            const float *S = M.sat2[box];           // cx, cz, hx, hz, reach
+            const float gap = fabsf(fmaf(dx, mz - S[1], -dz * (mx - S[0]))) - fmaf(S[2], fabsf(dz), S[3] * fabsf(dx));
+            apart[box] = gap > S[4] * nn;
+        }
+    }
+    // The reach (collision margin + capsule radius + box margin) depends on the link only, the boxes on nothing: the link's
+    // extents are grown by the reach and compared with per-box constants that stay in uniform registers for all links.
+    const float r = M.box_reach[l];
+    const float zr = zmin - r, xlo = minx - r, xhi = maxx + r, ylo = miny - r, yhi = maxy + r;
+#pragma unroll
+    for (int box = 0; box < 2; box++) {
+        const float *K = M.box_k[box];              // ztop, cx, hx, hy, cx - hx, cx + hx, -hy, hy   (cy = 0)
+        const bool near_z = zr <= K[0];
+        const bool over = fabsf(Lx - K[1]) <= K[2] && fabsf(Ly) <= K[3];
+        const bool beside = xhi >= K[4] && xlo <= K[5] && yhi >= K[6] && ylo <= K[7];
+        hit = hit || (near_z && over);
+        if (near_z && !over && beside && !apart[box]) slow |= 1u << (2 * (l - 2) + box);
+    }
+}
 template <int TASK, bool WORKBENCH>
 URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const ObstW &O, bool collide, float *ee,
                                  float *dist, float *cap, int cs) {
+    // Where the table / track tests run.  In the chain walk (end points still in registers, no link loop at all for
+    // UR5OriReach) they cost the fewest instructions: Ori -11 %, Obs -2.7 %, Sta -1 % kernel time.  UR5DynReach keeps them
+    // in the link loop: its walk already carries the most live state, and the 300 extra static instructions pushed its
+    // instruction-fetch stalls from 0.66 to 1.17 warps per issue slot (+1.5 %, measured with 3.5 % fewer instructions).
+#ifdef URGYM_BOX_IN_LOOP
+    constexpr bool BOX_IN_LOOP = URGYM_BOX_IN_LOOP != 0;
+#else
+    constexpr bool BOX_IN_LOOP = TASK == TASK_DYN;
+#endif
     PoseP T;
     posep_identity(T);
+    bool hit = false;
+    unsigned slow = 0u;
 #pragma unroll
     for (int l = 1; l < 7; l++) {
         if (l == 1) fkp_first(M, T, q[0]);          // from the identity pose: a third of the general step
@@ -490,56 +542,24 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
             capsule_world(M, T, l, axy, bxy, abz);
             float *c = cap + (l - 1) * 6 * cs;
             c[0] = axy.x; c[cs] = axy.y; c[2 * cs] = abz.x; c[3 * cs] = bxy.x; c[4 * cs] = bxy.y; c[5 * cs] = abz.y;
+            if (!BOX_IN_LOOP && l >= 2) box_tests(M, l, f3(axy.x, axy.y, abz.x), f3(bxy.x, bxy.y, abz.y), hit, slow);
         }
     }
     float3 e = euler_from_posep(T);
     ee[0] = T.pxy.x; ee[1] = T.pxy.y; ee[2] = T.pz; ee[3] = e.x; ee[4] = e.y; ee[5] = e.z;
     if (!collide) return false;
-    bool hit = false;
-    unsigned slow = 0u;
-    // links 2..6 vs obstacle (distances kept: they are get_link_distances' values), table and track
-#pragma unroll 2     // two links per trip: their dependent chains interleave (-0.8 %); fully unrolled it spills (-21 %)
-    for (int l = 2; l < 7; l++) {
-        const float *c = cap + (l - 1) * 6 * cs;
-        const float3 a = f3(c[0], c[cs], c[2 * cs]), b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
-        if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
-            float d = sqrtf(seg_axis_dist2(a, b, O.c, O.u, M.fit_obst_h, M.cap_ia[l])) - M.fit_obst[l];
-            hit = hit || (d <= URGYM_COLLISION_MARGIN);
-            cap[(36 + l - 2) * cs] = d;
-        }
-        // Table and track (pyb_setup.py:408-417), branch-free for the common cases.  With L the lower end point of
-        // the segment and dz = L.z - (top face of the box core): dz > reach means the whole segment is farther than
-        // `reach` above the box, no hit; otherwise, if L lies over the box's footprint, dist(segment, box) <=
-        // dist(L, box) = max(dz, 0) <= reach, a hit.  Only a low segment whose lower end is beside the footprint
-        // (table edges, most track cases) needs the exact segment-box distance; those are collected in `slow`.
-        {
-            const bool a_low = a.z <= b.z;
-            const float Lx = a_low ? a.x : b.x, Ly = a_low ? a.y : b.y, zmin = fminf(a.z, b.z);
-            const float minx = fminf(a.x, b.x), maxx = fmaxf(a.x, b.x), miny = fminf(a.y, b.y), maxy = fmaxf(a.y, b.y);
-            // Upper arm only (a warp-uniform branch): in steady state three quarters of the `slow` cases are the upper arm
-            // hanging down beside the track or behind the table, and 87 % of those are no hits.  The axis n = d x e_y
-            // (perpendicular to the segment and to the boxes' long edges) separates every one of them: the segment
-            // projects to a point, the box to |n_x| hx + |n_z| hz, and a gap beyond `reach` is a proven miss.
-            bool apart[2] = {false, false};
-            if (l == 2) {
-                const float dx = b.x - a.x, dz = b.z - a.z, mx = 0.5f * (a.x + b.x), mz = 0.5f * (a.z + b.z);
-                const float nn = sqrtf(fmaf(dx, dx, dz * dz));
-#pragma unroll
-                for (int box = 0; box < 2; box++) {
-                    const float *S = M.sat2[box];           // cx, cz, hx, hz, reach
-                    const float gap = fabsf(fmaf(dx, mz - S[1], -dz * (mx - S[0]))) - fmaf(S[2], fabsf(dz), S[3] * fabsf(dx));
-                    apart[box] = gap > S[4] * nn;
-                }
+    // links 2..6 vs obstacle (distances kept: they are get_link_distances' values)
+    if (BOX_IN_LOOP || Traits<TASK>::HAS_OBST) {
+#pragma unroll 2     // two links per trip: their dependent chains interleave (rolled: +10 % kernel time; fully unrolled it spills)
+        for (int l = 2; l < 7; l++) {
+            const float *c = cap + (l - 1) * 6 * cs;
+            const float3 a = f3(c[0], c[cs], c[2 * cs]), b = f3(c[3 * cs], c[4 * cs], c[5 * cs]);
+            if (Traits<TASK>::HAS_OBST) {       // keys[5] == 'obstacle'   pyb_setup.py:398-399
+                float d = sqrtf(seg_axis_dist2(a, b, O.c, O.u, M.fit_obst_h, M.cap_ia[l])) - M.fit_obst[l];
+                hit = hit || (d <= URGYM_COLLISION_MARGIN);
+                cap[(36 + l - 2) * cs] = d;
             }
-#pragma unroll
-            for (int box = 0; box < 2; box++) {
-                const float *L = M.box_lim[l][box];         // zthr, cx, cy, hx, hy, xlo, xhi, ylo, yhi
-                const bool near_z = zmin <= L[0];
-                const bool over = fabsf(Lx - L[1]) <= L[3] && fabsf(Ly - L[2]) <= L[4];
-                const bool beside = maxx >= L[5] && minx <= L[6] && maxy >= L[7] && miny <= L[8];
-                hit = hit || (near_z && over);
-                if (near_z && !over && beside && !apart[box]) slow |= 1u << (2 * (l - 2) + box);
-            }
+            if (BOX_IN_LOOP) box_tests(M, l, a, b, hit, slow);
         }
     }
     while (slow) {          // exact segment-box distance for the few (link, box) cases left

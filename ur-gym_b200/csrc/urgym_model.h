@@ -113,14 +113,14 @@ static void build_model_const(ModelConst &M) {
             M.self_reach2[p] = reach * reach;
         }
     }
-    for (int l = 0; l < 7; l++)
-        for (int b = 0; b < 2; b++) {
-            const float reach = 0.01f + M.fit_box[l] + M.box_margin[b];                 // 0.01 = URGYM_COLLISION_MARGIN
-            const float cx = M.box_c[b][0], cy = M.box_c[b][1], hx = M.box_he[b][0], hy = M.box_he[b][1];
-            float *L = M.box_lim[l][b];
-            L[0] = M.box_c[b][2] + M.box_he[b][2] + reach; L[1] = cx; L[2] = cy; L[3] = hx; L[4] = hy;
-            L[5] = cx - hx - reach; L[6] = cx + hx + reach; L[7] = cy - hy - reach; L[8] = cy + hy + reach;
-        }
+    // both boxes are centred on y = 0 and share one margin (reach.py:169-170): box_tests relies on it
+    for (int l = 0; l < 8; l++) M.box_reach[l] = l < 7 ? 0.01f + M.fit_box[l] + M.box_margin[0] : 0.0f;   // 0.01 = URGYM_COLLISION_MARGIN
+    for (int b = 0; b < 2; b++) {
+        const float cx = M.box_c[b][0], hx = M.box_he[b][0], hy = M.box_he[b][1];
+        float *K = M.box_k[b];
+        K[0] = M.box_c[b][2] + M.box_he[b][2]; K[1] = cx; K[2] = hx; K[3] = hy;
+        K[4] = cx - hx; K[5] = cx + hx; K[6] = -hy; K[7] = hy;
+    }
     for (int b = 0; b < 2; b++) {
         float *S = M.sat2[b];
         S[0] = M.box_c[b][0]; S[1] = M.box_c[b][2]; S[2] = M.box_he[b][0]; S[3] = M.box_he[b][2];
