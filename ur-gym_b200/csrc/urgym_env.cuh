@@ -351,11 +351,12 @@ template <> struct LinkShape<GEOM_HULL> {
         H.aoff = hull_adj_off(hv) + M.hull_off[l]; H.adj = hull_adj(hv); H.start = M.hull_start[l]; H.cur = -1;
         return H;
     }
-    URGYM_HD float obstacle_dist(const ModelConst &M, int l, const ObstW &O) const {
-        // GJK converges only sublinearly against the curved wall of a cylinder (hundreds of iterations for 1e-6).
-        // Against the cylinder's AXIS SEGMENT the problem is polytope-polytope and terminates in a few iterations;
-        // when the closest vector comes out perpendicular to the axis, the nearest cylinder point lies on the side
-        // wall and distance(hull, cylinder) = distance(hull, axis segment) - radius exactly.
+    // link <-> obstacle distance in two stages (the hull-geometry step kernel runs the second one as a compacted task):
+    // GJK converges only sublinearly against the curved wall of a cylinder (hundreds of iterations for 1e-6).
+    // Against the cylinder's AXIS SEGMENT the problem is polytope-polytope and terminates in a few iterations;
+    // when the closest vector comes out perpendicular to the axis, the nearest cylinder point lies on the side
+    // wall and distance(hull, cylinder) = distance(hull, axis segment) - radius exactly.
+    URGYM_HD bool obstacle_dist_side(const ModelConst &M, int l, const ObstW &O, float &d) const {
         bool deep;
         float3 v;
         float lb;
@@ -364,12 +365,25 @@ template <> struct LinkShape<GEOM_HULL> {
         float ds = gjk_distance(H, S, deep, &v, &lb);
         if (!deep && ds > M.obst_r && fabsf(dot(v, O.u)) <= 1e-5f * ds) {
             if (ds - lb > URGYM_GJK_REFINE_GAP) ds = gjk_distance_refine(H, S, v);
-            return ds - M.obst_r - M.hull_margin - M.obst_margin;
+            d = ds - M.obst_r - M.hull_margin - M.obst_margin;
+            return true;
         }
-        CylW C; C.c = O.c; C.u = O.u; C.r = M.obst_r; C.h = M.obst_h;      // end caps / rims / penetration
+        return false;
+    }
+    URGYM_HD float obstacle_dist_caps(const ModelConst &M, int l, const ObstW &O) const {      // end caps / rims / penetration
+        bool deep;
+        float3 v;
+        float lb;
+        const HullW H = hull(M, l);
+        CylW C; C.c = O.c; C.u = O.u; C.r = M.obst_r; C.h = M.obst_h;
         float d = gjk_distance(H, C, deep, &v, &lb);
         if (!deep && d - lb > URGYM_GJK_REFINE_GAP) d = gjk_distance_refine(H, C, v);
         return d - M.hull_margin - M.obst_margin;
+    }
+    URGYM_HD float obstacle_dist(const ModelConst &M, int l, const ObstW &O) const {
+        float d;
+        if (obstacle_dist_side(M, l, O, d)) return d;
+        return obstacle_dist_caps(M, l, O);
     }
     URGYM_HD float box_dist(const ModelConst &M, int l, int box) const {      // link-distance mode "workbench"
         BoxA B; B.c = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
@@ -380,8 +394,8 @@ template <> struct LinkShape<GEOM_HULL> {
         if (!deep && d - lb > URGYM_GJK_REFINE_GAP) d = gjk_distance_refine(H, B, v);
         return d - M.hull_margin - M.box_margin[box];
     }
-    URGYM_HD bool box_hit(const ModelConst &M, int l, int box) const {
-        if (!cap.box_hit(M, l, box)) return false;
+    // the exact halves of the collision booleans: run where the capsule broad phase (cap.box_hit / cap.link_hit) cannot decide
+    URGYM_HD bool box_hit_exact(const ModelConst &M, int l, int box) const {
         BoxA B; B.c = f3(M.box_c[box][0], M.box_c[box][1], M.box_c[box][2]);
         B.he = f3(M.box_he[box][0], M.box_he[box][1], M.box_he[box][2]);
         bool deep; float3 v; float lb;
@@ -391,14 +405,17 @@ template <> struct LinkShape<GEOM_HULL> {
         if (!deep && d - lb > URGYM_GJK_REFINE_GAP && fabsf(d - thr) < 1e-3f) d = gjk_distance_refine(H, B, v);   // undecided near the threshold
         return d <= thr;
     }
-    URGYM_HD bool link_hit(const ModelConst &M, int l, int l2, const LinkShape &o) const {
-        if (!cap.link_hit(M, l, l2, o.cap)) return false;
+    URGYM_HD bool link_hit_exact(const ModelConst &M, int l, int l2, const LinkShape &o) const {
         bool deep; float3 v; float lb;
         const HullW H1 = hull(M, l), H2 = o.hull(M, l2);
         float d = gjk_distance(H1, H2, deep, &v, &lb);
         const float thr = URGYM_COLLISION_MARGIN + 2.0f * M.hull_margin;
         if (!deep && d - lb > URGYM_GJK_REFINE_GAP && fabsf(d - thr) < 1e-3f) d = gjk_distance_refine(H1, H2, v);
         return d <= thr;
+    }
+    URGYM_HD bool box_hit(const ModelConst &M, int l, int box) const { return cap.box_hit(M, l, box) && box_hit_exact(M, l, box); }
+    URGYM_HD bool link_hit(const ModelConst &M, int l, int l2, const LinkShape &o) const {
+        return cap.link_hit(M, l, l2, o.cap) && link_hit_exact(M, l, l2, o);
     }
 };
 
@@ -687,18 +704,20 @@ URGYM_HD bool goal_metrics(const float *ee, const float *E, const float *C, floa
 }
 
 // ------------------------------------------------------------------------------------------------ step
-// RobotTaskEnv.step (core.py:303-317) + TimeLimit, without the auto-reset.  `row` receives the observation
-// (OBS floats).  vel_out (Dyn, 6 floats): ReachDyn.velocity after this step.
+// RobotTaskEnv.step (core.py:303-317) + TimeLimit, without the auto-reset, in three parts: env_step_begin (action,
+// obstacle motion), the robot pass (FK, collision, link distances), env_step_finish (observation, termination, reward).
+// The hull-geometry step kernel runs its own robot pass between the two (urgym_kernels.cuh: the exact GJK tests of a
+// whole block are compacted into dense task lists); everything else calls env_step.
+// `row` receives the observation (OBS floats).  vel_out (Dyn, 6 floats): ReachDyn.velocity after this step.
 template <int TASK, int GEOM>
-URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const float4 *hv, float *row, StepOut &o,
-                       float *vel_out, float *scratch, int cs) {
+URGYM_HD ObstW env_step_begin(EnvState &s, const float *act, float *row, float *vel_out, float *vel, float3 &oe) {
     typedef Traits<TASK> TT;
     // 1. UR5Ori.set_action: clip, * pi, * 0.1 (float32 like the numpy expression), teleport      UR5.py:273-279,314-317
 #pragma unroll
     for (int j = 0; j < 6; j++) s.q[j] += (clampf(act[j], -1.0f, 1.0f) * URGYM_PI_F) * 0.1f;
     // 2. task.set_velocity + sim.step: obstacle pose after this step (twist from the episode cache)   core.py:305-309
-    float3 oe;
-    float vel[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int k = 0; k < 6; k++) vel[k] = 0.0f;
     const ObstW O = obstacle_cached<TASK>(s.E, s.C, s.elapsed + 1, oe);
     if (TT::DYN) {
         if (s.elapsed < 25) {           // ReachDyn.velocity: the twist while step_num < 25, zeros afterwards
@@ -708,14 +727,15 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
 #pragma unroll
         for (int k = 0; k < 6; k++) vel_out[k] = vel[k];
     }
-    // 3. FK and collision                                                                      core.py:310
-    float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    if (URGYM_BASE(GEOM) != GEOM_CAPSULE) {
+    if (URGYM_BASE(GEOM) != GEOM_CAPSULE) {     // the rolled hull pass reads the joint angles from memory
 #pragma unroll
         for (int k = 0; k < 6; k++) row[6 + k] = s.q[k];
     }
-    bool coll = robot_pass<TASK, GEOM>(M, s.q, row + 6, O, hv, true, ee, dist, scratch, cs);
-    URGYM_WARP_SYNC();      // every lane is done with the scratch before observation rows are written over it
+    return O;
+}
+template <int TASK>
+URGYM_HD void env_step_finish(EnvState &s, float *row, const float *ee, const float *dist, bool coll, const ObstW &O, float3 oe,
+                              const float *vel, StepOut &o) {
     // 4. observation: carries link_dist from BEFORE this step's reward (quirk Q1)               core.py:311
     write_obs_row<TASK>(row, ee, s.q, s.E, O, oe, vel, s.ld);
     // 5. termination                                                                           core.py:313-315
@@ -758,6 +778,18 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
     s.elapsed += 1;
     o.truncated = s.elapsed >= URGYM_MAX_STEPS;
     s.ep_ret += r;
+}
+template <int TASK, int GEOM>
+URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const float4 *hv, float *row, StepOut &o,
+                       float *vel_out, float *scratch, int cs) {
+    float3 oe;
+    float vel[6];
+    const ObstW O = env_step_begin<TASK, GEOM>(s, act, row, vel_out, vel, oe);
+    // 3. FK and collision                                                                      core.py:310
+    float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    bool coll = robot_pass<TASK, GEOM>(M, s.q, row + 6, O, hv, true, ee, dist, scratch, cs);
+    URGYM_WARP_SYNC();      // every lane is done with the scratch before observation rows are written over it
+    env_step_finish<TASK>(s, row, ee, dist, coll, O, oe, vel, o);
 }
 
 // RobotTaskEnv._get_obs (core.py:252-261) from the current state, no stepping.  stale_vel: ReachDyn.velocity as

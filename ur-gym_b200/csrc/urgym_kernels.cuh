@@ -185,15 +185,137 @@ template <int GEOM> __device__ __forceinline__ const float4 *stage_hull(const fl
     for (int i = threadIdx.x; i < URGYM_HULL_BLOB_F4; i += blockDim.x) s[i] = g[i];
     return s;
 }
-// per-warp tile: 32 observation rows; the capsule pass's scratch column block [41][32] overlays it
-template <int TASK> struct TileFloats {
-    static constexpr int value = Traits<TASK>::OBS > URGYM_SCRATCH_FLOATS ? Traits<TASK>::OBS : URGYM_SCRATCH_FLOATS;
+// per-warp tile: 32 observation rows; the capsule pass's scratch column block [41][32] overlays it (capsule geometry only)
+template <int TASK, int GEOM> struct TileFloats {
+    static constexpr int value = (URGYM_BASE(GEOM) == GEOM_HULL || Traits<TASK>::OBS > URGYM_SCRATCH_FLOATS)
+                                     ? Traits<TASK>::OBS : URGYM_SCRATCH_FLOATS;
+};
+// Hull geometry: the exact GJK tests that the cheap stages of a block's 512 envs leave over, compacted into three dense
+// task lists in shared memory (hull_pass_phased).  A task is  env (bits 0..15) | link << 16 | (box or second link) << 20.
+#define URGYM_HULL_QCAP 2048
+struct HullTasks {
+    int count[4];                       // [0] link vs cylinder caps / rims  [1] link vs table / track  [2] self pairs
+    int list[3][URGYM_HULL_QCAP];
 };
 template <int TASK, int GEOM> constexpr size_t step_smem_bytes() {
-    return (size_t)Blk<GEOM>::STEP * TileFloats<TASK>::value * sizeof(float) +
-           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)URGYM_HULL_BLOB_F4 * sizeof(float4) : 0);
+    return (size_t)Blk<GEOM>::STEP * TileFloats<TASK, GEOM>::value * sizeof(float) +
+           (URGYM_BASE(GEOM) == GEOM_HULL ? (size_t)URGYM_HULL_BLOB_F4 * sizeof(float4) + sizeof(HullTasks) : 0);
 }
 __device__ __forceinline__ void stat_add(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }   // RED.E.ADD.64 (result unused)
+
+// ------------------------------------------------------------------------------------------------ hull geometry pass
+// The robot pass of the hull-geometry step kernel (same tests and arithmetic as robot_pass_rolled, urgym_env.cuh).  One
+// GJK per lane with data-dependent work kept 5 of 32 lanes busy: a few lanes of every warp need the cylinder's caps, the
+// exact table / track test or an exact self-collision test while the others wait.  Here every lane first runs only the
+// stages that all lanes run (the chain walk, GJK against the obstacle's axis segment, the capsule broad phases) and
+// queues what is left; then the whole block works through the three task lists with one task per lane, recomputing the
+// link pose from the env's joint angles (240 instructions against the thousands of a GJK); then every lane collects its
+// results.  Scratch per env, in its observation row until env_step_finish overwrites it: [0..5) link-obstacle
+// distances, [5] collision flag, [6..12) joint angles (env_step_begin), [12..18) obstacle centre and axis.
+static __device__ __noinline__ bool hull_self_exact(const ModelConst &M, const float *qrow, int l, int l2, const float4 *hv) {
+    Pose T;
+    pose_identity(T);
+    LinkShape<GEOM_HULL> a, b;
+    for (int j = 1; j <= l; j++) {
+        fk_advance(M, T, j - 1, qrow[j - 1]);
+        if (j == l2) b.set(M, l2, T, hv);
+    }
+    a.set(M, l, T, hv);
+    return a.link_hit_exact(M, l, l2, b);
+}
+template <int TASK, int GEOM>
+__device__ __forceinline__ bool hull_pass_phased(const ModelConst &M, float *rows, int tid, const ObstW &O, const float4 *hv,
+                                                 float *ee, float *dist, HullTasks &Q) {
+    typedef Traits<TASK> TT;
+    constexpr int D = TT::OBS;
+    float *row = rows + tid * D;
+    auto push = [&](int type, int code) {
+        const int slot = atomicAdd(&Q.count[type], 1);
+        if (slot < URGYM_HULL_QCAP) Q.list[type][slot] = code;
+        return slot < URGYM_HULL_QCAP;          // a full list: the caller does the test itself
+    };
+    Pose T;
+    pose_identity(T);
+    LinkShape<GEOM_CAPSULE> c1, c2, c3;
+    bool hit = false;
+    float wb[5] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+#pragma unroll 1
+    for (int l = 1; l < 7; l++) {
+        fk_advance(M, T, l - 1, row[6 + l - 1]);
+        LinkShape<GEOM_HULL> cur;
+        cur.set(M, l, T, hv);
+        if (l >= 2) {
+            if (TT::HAS_OBST) {
+                float d;
+                if (!cur.obstacle_dist_side(M, l, O, d)) {
+                    d = 3.0e38f;
+                    if (!push(0, tid | (l << 16))) d = cur.obstacle_dist_caps(M, l, O);
+                }
+                row[l - 2] = d;
+                if (URGYM_WB(GEOM)) {
+                    const float w = fminf(cur.box_dist(M, l, 0), cur.box_dist(M, l, 1));
+                    if (l == 2) wb[0] = w; else if (l == 3) wb[1] = w; else if (l == 4) wb[2] = w; else if (l == 5) wb[3] = w; else wb[4] = w;
+                }
+            }
+#pragma unroll 1
+            for (int box = 0; box < 2; box++)
+                if (cur.cap.box_hit(M, l, box) && !push(1, tid | (l << 16) | (box << 20))) hit = hit || cur.box_hit_exact(M, l, box);
+        }
+        if (l >= 3 && cur.cap.link_hit(M, l, 1, c1) && !push(2, tid | (l << 16) | (1 << 20))) hit = hit || hull_self_exact(M, row + 6, l, 1, hv);
+        if (l >= 4 && cur.cap.link_hit(M, l, 2, c2) && !push(2, tid | (l << 16) | (2 << 20))) hit = hit || hull_self_exact(M, row + 6, l, 2, hv);
+        if (l >= 5 && cur.cap.link_hit(M, l, 3, c3) && !push(2, tid | (l << 16) | (3 << 20))) hit = hit || hull_self_exact(M, row + 6, l, 3, hv);
+        if (l == 1) c1 = cur.cap; else if (l == 2) c2 = cur.cap; else if (l == 3) c3 = cur.cap;
+    }
+    const float3 e = euler_from_mat(T.R);
+    ee[0] = T.p.x; ee[1] = T.p.y; ee[2] = T.p.z; ee[3] = e.x; ee[4] = e.y; ee[5] = e.z;
+    row[5] = hit ? 1.0f : 0.0f;
+    if (TT::HAS_OBST) { row[12] = O.c.x; row[13] = O.c.y; row[14] = O.c.z; row[15] = O.u.x; row[16] = O.u.y; row[17] = O.u.z; }
+    __syncthreads();
+    const int nthreads = blockDim.x;
+    if (TT::HAS_OBST) {
+        const int n0 = min(Q.count[0], URGYM_HULL_QCAP);
+        for (int k = tid; k < n0; k += nthreads) {
+            const int code = Q.list[0][k], en = code & 0xFFFF, l = (code >> 16) & 15;
+            float *re = rows + en * D;
+            ObstW Oe = obstacle_none();
+            Oe.c = f3(re[12], re[13], re[14]); Oe.u = f3(re[15], re[16], re[17]);
+            Pose Tl;
+            fk_link(M, re + 6, l, Tl);
+            LinkShape<GEOM_HULL> L;
+            L.set(M, l, Tl, hv);
+            re[l - 2] = L.obstacle_dist_caps(M, l, Oe);
+        }
+    }
+    {
+        const int n1 = min(Q.count[1], URGYM_HULL_QCAP);
+        for (int k = tid; k < n1; k += nthreads) {
+            const int code = Q.list[1][k], en = code & 0xFFFF, l = (code >> 16) & 15, box = (code >> 20) & 1;
+            float *re = rows + en * D;
+            Pose Tl;
+            fk_link(M, re + 6, l, Tl);
+            LinkShape<GEOM_HULL> L;
+            L.set(M, l, Tl, hv);
+            if (L.box_hit_exact(M, l, box)) re[5] = 1.0f;
+        }
+        const int n2 = min(Q.count[2], URGYM_HULL_QCAP);
+        for (int k = tid; k < n2; k += nthreads) {
+            const int code = Q.list[2][k], en = code & 0xFFFF, l = (code >> 16) & 15, l2 = (code >> 20) & 3;
+            float *re = rows + en * D;
+            if (hull_self_exact(M, re + 6, l, l2, hv)) re[5] = 1.0f;
+        }
+    }
+    __syncthreads();
+    hit = row[5] != 0.0f;
+    if (TT::HAS_OBST) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float d = row[k];
+            hit = hit || (d <= URGYM_COLLISION_MARGIN);     // keys[5] == 'obstacle'   pyb_setup.py:398-404
+            dist[k] = URGYM_WB(GEOM) ? fminf(d, wb[k]) : d;
+        }
+    }
+    return hit;
+}
 
 // ------------------------------------------------------------------------------------------------ step
 // One env per thread; every warp owns a private 32-row tile of the observation array in shared memory and there is
@@ -204,10 +326,12 @@ template <int TASK, int GEOM>
 __global__ void __launch_bounds__(Blk<GEOM>::STEP, Blk<GEOM>::STEP_MINBLOCKS) urgym_step_kernel(const __grid_constant__ ModelConst c_model, const StepArgs A) {
     typedef Traits<TASK> TT;
     constexpr int D = TT::OBS, G = TT::GOAL, B = Blk<GEOM>::STEP, W = 32;
-    constexpr int TF = TileFloats<TASK>::value;
+    constexpr int TF = TileFloats<TASK, GEOM>::value;
+    constexpr bool HULL = URGYM_BASE(GEOM) == GEOM_HULL;
     extern __shared__ float4 smem4[];
     float *s_tiles = reinterpret_cast<float *>(smem4);        // [warps][32 * TF]: obs tile [32][D]
     float4 *s_hull = reinterpret_cast<float4 *>(s_tiles + B * TF);
+    HullTasks *s_tasks = reinterpret_cast<HullTasks *>(s_hull + URGYM_HULL_BLOB_F4);      // hull geometry only
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (blockIdx.x == 0 && tid == 0) {                          // this launch is reset event number event[chain] + 1
@@ -219,17 +343,20 @@ __global__ void __launch_bounds__(Blk<GEOM>::STEP, Blk<GEOM>::STEP_MINBLOCKS) ur
         }
     }
     const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
-    if (URGYM_BASE(GEOM) == GEOM_HULL) __syncthreads();
+    if (HULL) {
+        if (tid < 4) s_tasks->count[tid] = 0;
+        __syncthreads();
+    }
 
     const int64_t wbase = (int64_t)blockIdx.x * B + warp * W;                 // first env of this warp
-    if (wbase >= A.n) return;
-    const int rows = (A.n - wbase) < W ? (int)(A.n - wbase) : W;
+    if (!HULL && wbase >= A.n) return;                       // (hull geometry: every warp of the block takes part in its barriers)
+    const int rows = wbase >= A.n ? 0 : ((A.n - wbase) < W ? (int)(A.n - wbase) : W);
     float *s_obs = s_tiles + warp * W * TF;
     float *s_scr = s_obs + lane;                              // capsule scratch: column `lane` of a [41][32] block
 
     // every lane runs the step (warp-level barriers inside); lanes past the end redo the last env and store nothing
     const bool live = lane < rows;
-    const int64_t i = wbase + (live ? lane : rows - 1);
+    const int64_t i = live ? wbase + lane : (rows ? wbase + rows - 1 : A.n - 1);
     EnvState s;
     StepOut o;
     float vel[6], act[6];
@@ -246,7 +373,16 @@ __global__ void __launch_bounds__(Blk<GEOM>::STEP, Blk<GEOM>::STEP_MINBLOCKS) ur
     }
     load_dyn<TASK>(A.st, i, s);
     load_hot<TASK>(A.st, i, s);
-    env_step<TASK, GEOM>(c_model, s, act, hv, s_obs + lane * D, o, vel, s_scr, W);
+    if (HULL) {
+        float3 oe;
+        float velv[6], ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        const ObstW O = env_step_begin<TASK, GEOM>(s, act, s_obs + lane * D, vel, velv, oe);
+        const bool coll = hull_pass_phased<TASK, GEOM>(c_model, s_tiles, tid, O, hv, ee, dist, *s_tasks);
+        env_step_finish<TASK>(s, s_obs + lane * D, ee, dist, coll, O, oe, velv, o);
+        if (rows == 0) return;
+    } else {
+        env_step<TASK, GEOM>(c_model, s, act, hv, s_obs + lane * D, o, vel, s_scr, W);
+    }
     if (live) {
         store_dyn<TASK>(A.st, i, s);
         A.rew[i] = o.reward;
