@@ -142,8 +142,6 @@ struct alignas(16) ModelConst {
     float fit_obst_h, fit_obst_ie;
     float box_top;              // highest top face of the table / track cores (z), for the height broad phase
     int hull_off[8];            // vertex ranges of links 0..6 inside the packed float4 vertex array
-    unsigned short hull_start[7][8];    // per link and octant of the (link-frame) direction: support vertex of the octant's
-                                        // diagonal, where the hill-climbing support function starts its first walk
     // margins of Bullet's GJK pair detector (distance = |core gap| - marginA - marginB)
     float hull_margin;          // URDF mesh links: 0.001
     float box_c[2][3], box_he[2][3], box_margin[2];    // 0 = table, 1 = track; core half extents (shrunk by the margin)
@@ -484,42 +482,77 @@ URGYM_HD void euler_obstacle(float u_sign, float u_roll, float u_pitch, float &r
 #define URGYM_HULL_NADJ 22674
 #define URGYM_HULL_OFF_U16 3800                     /* NV + 1 offsets, padded to a multiple of 8 */
 #define URGYM_HULL_ADJ_U16 22680                    /* padded to a multiple of 8 */
-#define URGYM_HULL_BLOB_F4 (URGYM_HULL_NV + (URGYM_HULL_OFF_U16 + URGYM_HULL_ADJ_U16) / 8)
+// ... then the start table of the hill-climbing support function: per link, for each cell of an 8 x 8 grid on each face of
+// the direction cube (link frame), the support vertex of the cell's centre direction (LOCAL index), built at create time.
+#define URGYM_HULL_DIR_CELLS 384                    /* 6 faces x 8 x 8 */
+#define URGYM_HULL_DIR_U16 (7 * URGYM_HULL_DIR_CELLS)
+#define URGYM_HULL_BLOB_F4 (URGYM_HULL_NV + (URGYM_HULL_OFF_U16 + URGYM_HULL_ADJ_U16 + URGYM_HULL_DIR_U16) / 8)
 URGYM_HD const unsigned short *hull_adj_off(const float4 *blob) { return reinterpret_cast<const unsigned short *>(blob + URGYM_HULL_NV); }
 URGYM_HD const unsigned short *hull_adj(const float4 *blob) { return hull_adj_off(blob) + URGYM_HULL_OFF_U16; }
+URGYM_HD const unsigned short *hull_dirmap(const float4 *blob) { return hull_adj(blob) + URGYM_HULL_ADJ_U16; }
+// cell of direction l on the direction cube: face = dominant axis and sign, (u, v) = the other two components / |dominant|
+URGYM_HD int hull_dir_cell(float3 l) {
+    const float ax = fabsf(l.x), ay = fabsf(l.y), az = fabsf(l.z);
+    int face; float m, u, v;
+    if (ax >= ay && ax >= az) { face = l.x > 0.0f ? 0 : 1; m = ax; u = l.y; v = l.z; }
+    else if (ay >= az) { face = l.y > 0.0f ? 2 : 3; m = ay; u = l.x; v = l.z; }
+    else { face = l.z > 0.0f ? 4 : 5; m = az; u = l.x; v = l.y; }
+    if (!(m > 0.0f)) return 0;
+    const float k = 4.0f / m;
+    int iu = (int)fmaf(u, k, 4.0f), iv = (int)fmaf(v, k, 4.0f);
+    iu = iu < 0 ? 0 : (iu > 7 ? 7 : iu); iv = iv < 0 ? 0 : (iv > 7 ? 7 : iv);
+    return face * 64 + iv * 8 + iu;
+}
+// centre direction of a cell (host side, table construction)
+inline void hull_cell_dir(int cell, double d[3]) {
+    const int face = cell / 64, iv = (cell / 8) % 8, iu = cell % 8;
+    const double u = (iu + 0.5) / 4.0 - 1.0, v = (iv + 0.5) / 4.0 - 1.0, sg = (face & 1) ? -1.0 : 1.0;
+    if (face < 2) { d[0] = sg; d[1] = u; d[2] = v; }
+    else if (face < 4) { d[0] = u; d[1] = sg; d[2] = v; }
+    else { d[0] = u; d[1] = v; d[2] = sg; }
+}
 
-struct HullW {                      // link hull: vertices in the link frame (shared memory), posed by T
-    const float4 *v; int n; const Pose *T;
-    const unsigned short *aoff, *adj;       // adjacency of THIS link: aoff[k] .. aoff[k + 1] index adj (local neighbour ids)
-    const unsigned short *start;            // ModelConst::hull_start of this link
-    mutable int cur;                        // last support vertex: the next query starts its walk there (-1: none yet)
-    URGYM_HD float3 center() const { return T->p; }
-    // Support vertex by steepest ascent over the hull's edges: on a convex polytope a vertex with no better neighbour is
-    // the maximum.  Consecutive GJK directions are close, so after the first query the walk is one or two edges long
-    // (the exhaustive scan of round 1 looked at all 73..998 vertices of the link in every query).
-    URGYM_HD float3 support(float3 d) const { return hull_support(*this, d); }
-    static URGYM_OOL float3 hull_support(const HullW &H, float3 d) { return H.support_impl(d); }
-    URGYM_HD float3 support_impl(float3 d) const {
-        const float3 l = rotT(T->R, d);
-        int c = cur;
-        if (c < 0) c = start[(l.x > 0.0f ? 1 : 0) | (l.y > 0.0f ? 2 : 0) | (l.z > 0.0f ? 4 : 0)];   // first query of this hull
-        float4 p = v[c];
-        float best = fmaf(p.x, l.x, fmaf(p.y, l.y, p.z * l.z));
-        for (int it = 0; it < n; it++) {
-            int nxt = -1;
-            const int e1 = aoff[c + 1];
-            for (int e = aoff[c]; e < e1; e++) {
-                const int k = adj[e];
-                const float4 q = v[k];
-                const float s = fmaf(q.x, l.x, fmaf(q.y, l.y, q.z * l.z));
-                if (s > best) { best = s; nxt = k; }
-            }
-            if (nxt < 0) break;
-            c = nxt;
+// Support vertex of a link hull by steepest ascent over its edges: on a convex polytope a vertex with no better
+// neighbour is the maximum.  l: direction in the link frame.  Starts from the table's vertex for l (the exact support
+// vertex of a direction a few degrees away) or from the previous query's vertex `cur` when that one is better.
+// Out of line with every argument and the result in registers: handing it the hull by reference had put the link pose and
+// the hull descriptor of every caller into local memory, and with 215 KB of the SM's 256 KB configured as shared memory
+// the 512 threads' stack frames do not fit the remaining L1 (long-scoreboard stall 6.8 warps per issue slot).
+static URGYM_OOL int hull_climb(const float4 *v, const unsigned short *aoff, const unsigned short *adj,
+                                const unsigned short *start, int n, int cur, float lx, float ly, float lz) {
+    int c = start[hull_dir_cell(f3(lx, ly, lz))];
+    float4 p = v[c];
+    float best = fmaf(p.x, lx, fmaf(p.y, ly, p.z * lz));
+    if (cur >= 0) {
+        const float4 pc = v[cur];
+        const float sc = fmaf(pc.x, lx, fmaf(pc.y, ly, pc.z * lz));
+        if (sc > best) { best = sc; c = cur; }
+    }
+    for (int it = 0; it < n; it++) {
+        int nxt = -1;
+        const int e1 = aoff[c + 1];
+        for (int e = aoff[c]; e < e1; e++) {
+            const int k = adj[e];
+            const float4 q = v[k];
+            const float s = fmaf(q.x, lx, fmaf(q.y, ly, q.z * lz));
+            if (s > best) { best = s; nxt = k; }
         }
-        cur = c;
-        p = v[c];
-        return rot(T->R, f3(p.x, p.y, p.z)) + T->p;
+        if (nxt < 0) break;
+        c = nxt;
+    }
+    return c;
+}
+struct HullW {                      // link hull: vertices in the link frame (shared memory), posed by T (held by value)
+    const float4 *v; int n; Pose T;
+    const unsigned short *aoff, *adj;       // adjacency of THIS link: aoff[k] .. aoff[k + 1] index adj (local neighbour ids)
+    const unsigned short *start;            // start table of this link (hull_dirmap)
+    mutable int cur;                        // last support vertex: the next query starts its walk there (-1: none yet)
+    URGYM_HD float3 center() const { return T.p; }
+    URGYM_HD float3 support(float3 d) const {
+        const float3 l = rotT(T.R, d);
+        cur = hull_climb(v, aoff, adj, start, n, cur, l.x, l.y, l.z);
+        const float4 p = v[cur];
+        return rot(T.R, f3(p.x, p.y, p.z)) + T.p;
     }
 };
 struct SegW {                       // capsule core: a segment in world space
@@ -789,7 +822,7 @@ static URGYM_OOL bool closest_simplex_d(D3 (&W)[4], int &n, D3 &v) {
 #define URGYM_GJK_REFINE_ITER 256
 #define URGYM_GJK_REFINE_GAP 2.0e-6f      /* FP32 result accepted when its distance is proven to this (lower bound known) */
 template <class SA, class SB>
-static URGYM_OOL float gjk_distance_refine(const SA &A, const SB &B, float3 v0) {
+static URGYM_OOL float gjk_distance_refine(const SA A, const SB B, float3 v0) {     // shapes by value: the callers' stay in registers
     D3 W[4];
     int n = 1;
     float3 vf = v0;

@@ -347,8 +347,8 @@ template <> struct LinkShape<GEOM_HULL> {
         T.p = f3(M.neutral_p[l][0], M.neutral_p[l][1], M.neutral_p[l][2]);
     }
     URGYM_HD HullW hull(const ModelConst &M, int l) const {
-        HullW H; H.v = hv + M.hull_off[l]; H.n = M.hull_off[l + 1] - M.hull_off[l]; H.T = &T;
-        H.aoff = hull_adj_off(hv) + M.hull_off[l]; H.adj = hull_adj(hv); H.start = M.hull_start[l]; H.cur = -1;
+        HullW H; H.v = hv + M.hull_off[l]; H.n = M.hull_off[l + 1] - M.hull_off[l]; H.T = T;
+        H.aoff = hull_adj_off(hv) + M.hull_off[l]; H.adj = hull_adj(hv); H.start = hull_dirmap(hv) + l * URGYM_HULL_DIR_CELLS; H.cur = -1;
         return H;
     }
     // link <-> obstacle distance in two stages (the hull-geometry step kernel runs the second one as a compacted task):

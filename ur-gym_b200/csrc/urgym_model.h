@@ -40,6 +40,19 @@ static void build_hull_blob(float4 *out) {
     unsigned short *off = reinterpret_cast<unsigned short *>(out + URGYM_HULL_NV), *adj = off + URGYM_HULL_OFF_U16;
     for (int i = 0; i <= URGYM_HULL_NV; i++) off[i] = UR5E_HULL_ADJ_OFF[i];
     for (int i = 0; i < URGYM_HULL_NADJ; i++) adj[i] = UR5E_HULL_ADJ[i];
+    // start table of the support function: exact support vertex of every cell-centre direction, per link
+    unsigned short *dir = adj + URGYM_HULL_ADJ_U16;
+    for (int l = 0; l < 7; l++)
+        for (int cell = 0; cell < URGYM_HULL_DIR_CELLS; cell++) {
+            double d[3];
+            hull_cell_dir(cell, d);
+            int best = 0; double bv = -1e300;
+            for (int i = UR5E_HULL_OFFSET[l]; i < UR5E_HULL_OFFSET[l + 1]; i++) {
+                const double v = UR5E_HULL_VERTS[3 * i] * d[0] + UR5E_HULL_VERTS[3 * i + 1] * d[1] + UR5E_HULL_VERTS[3 * i + 2] * d[2];
+                if (v > bv) { bv = v; best = i - UR5E_HULL_OFFSET[l]; }
+            }
+            dir[l * URGYM_HULL_DIR_CELLS + cell] = (unsigned short)best;
+        }
 }
 
 static void build_model_const(ModelConst &M) {
@@ -69,16 +82,6 @@ static void build_model_const(ModelConst &M) {
         M.cap_ia[l] = (float)(1.0 / hl);
     }
     for (int l = 0; l < 8; l++) M.hull_off[l] = UR5E_HULL_OFFSET[l];
-    for (int l = 0; l < 7; l++)
-        for (int o = 0; o < 8; o++) {
-            const double dx = (o & 1) ? 1.0 : -1.0, dy = (o & 2) ? 1.0 : -1.0, dz = (o & 4) ? 1.0 : -1.0;
-            int best = 0; double bv = -1e300;
-            for (int i = UR5E_HULL_OFFSET[l]; i < UR5E_HULL_OFFSET[l + 1]; i++) {
-                const double v = UR5E_HULL_VERTS[3 * i] * dx + UR5E_HULL_VERTS[3 * i + 1] * dy + UR5E_HULL_VERTS[3 * i + 2] * dz;
-                if (v > bv) { bv = v; best = i - UR5E_HULL_OFFSET[l]; }
-            }
-            M.hull_start[l][o] = (unsigned short)best;
-        }
     M.hull_margin = (float)hull_margin;
     const double pm = 0.001;                                // createCollisionShape primitives: margin 0.001, core shrunk
     // create_table(1.1, 1.8, 0.92, x_offset=0.5, z_offset=-0.12)   reach.py:169; pyb_setup.py:802-811
