@@ -171,13 +171,16 @@ __device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_c
 #ifndef URGYM_HULL_BLOCK
 #define URGYM_HULL_BLOCK 512
 #endif
+#ifndef URGYM_HULL_AUTORESET_BLOCK
+#define URGYM_HULL_AUTORESET_BLOCK 128  /* every block stages the hull blob: 32 -> 568 us, 64 -> 377, 128 -> 254, 256 -> 264 (262144 Dyn envs) */
+#endif
 // Block sizes.  Capsule geometry: 128-thread blocks, six resident per SM.  Hull geometry: every block stages the 111 KB
 // hull blob (vertices + adjacency, urgym_device.cuh) in shared memory, so one big block per SM shares one copy.
 template <int GEOM> struct Blk {
     static constexpr bool HULL = URGYM_BASE(GEOM) == GEOM_HULL;
     static constexpr int STEP = HULL ? URGYM_HULL_BLOCK : URGYM_STEP_BLOCK;
     static constexpr int STEP_MINBLOCKS = HULL ? 1 : URGYM_STEP_MINBLOCKS;
-    static constexpr int AUTORESET = HULL ? 256 : URGYM_AUTORESET_BLOCK;
+    static constexpr int AUTORESET = HULL ? URGYM_HULL_AUTORESET_BLOCK : URGYM_AUTORESET_BLOCK;
 };
 // stage the hull blob in shared memory (hull mode only): the hill-climbing support function gathers from it per lane
 template <int GEOM> __device__ __forceinline__ const float4 *stage_hull(const float4 *g, float4 *s) {
