@@ -205,6 +205,35 @@ int64_t urgym_launch_count(const urgym_env_t *h);
 int urgym_profile_enable(urgym_env_t *h, int enabled);
 int urgym_profile_read(urgym_env_t *h, double *step_kernel_ms, double *reset_kernel_ms, int *steps);
 
+/* ---- the motor-driven robot path ------------------------------------------------------------ */
+/* `UR5IAIReach-v1` (UR_gym/envs/ur_tasks.py:10-21): robot `UR5` (UR_gym/envs/robots/UR5.py:10-118, urdf/ur5.urdf), task
+ * `ReachIAI` (UR_gym/envs/tasks/reach.py:9-66), N envs at once.  The one registered env of the reference whose step goes
+ * through setJointMotorControlArray(POSITION_CONTROL) (pyb_setup.py:365-380) and 20 dynamic substeps (pyb_setup.py:52-55)
+ * instead of a joint teleport.  Observation [N,6] = ee position + ee linear velocity (UR5.py:92-97), goals [N,3].
+ * Bullet's substep (forward dynamics, motor rows, 50 Gauss-Seidel sweeps, semi-implicit Euler) is restated from its
+ * published algorithm and is NOT pinned to a PyBullet run: oracle/ur_motor_oracle.c lists what is recalled; joint-limit
+ * and contact rows are not modelled.  A handle of its own: nothing here touches urgym_env_t. */
+typedef struct urgym_motor urgym_motor_t;
+enum { URGYM_MOTOR_F_Q = 0,        /* float [N,6] joint angles      (robot.set_joint_angles, core.py:161-167) */
+       URGYM_MOTOR_F_QD = 1,       /* float [N,6] joint velocities                                            */
+       URGYM_MOTOR_F_GOAL = 2,     /* float [N,3] goal              (task.set_goal)                           */
+       URGYM_MOTOR_F_ELAPSED = 3,  /* int32 [N]   TimeLimit counter                                           */
+       URGYM_MOTOR_F_COUNT = 4 };
+#define URGYM_MOTOR_OBS_DIM 6
+#define URGYM_MOTOR_GOAL_DIM 3
+int urgym_motor_create(urgym_motor_t **out, int64_t n_envs, int64_t env_index_offset, uint64_t seed, int device);
+int urgym_motor_destroy(urgym_motor_t *h);
+const char *urgym_motor_last_error(const urgym_motor_t *h);
+/* RobotTaskEnv.reset (core.py:263-273): neutral pose at rest (UR5.py:99-103), new goal (reach.py:48-57); mask NULL = all */
+int urgym_motor_reset(urgym_motor_t *h, const uint8_t *mask, float *obs, float *achieved, float *desired, void *stream);
+/* RobotTaskEnv.step (core.py:303-317) + TimeLimit(100), then auto-reset of the finished envs (terminal rows kept) */
+int urgym_motor_step(urgym_motor_t *h, const float *actions, float *obs, float *achieved, float *desired, float *reward,
+                     uint8_t *terminated, uint8_t *truncated, uint8_t *is_success, float *terminal_obs, void *stream);
+int urgym_motor_get_state(urgym_motor_t *h, int field, void *dst, void *stream);
+int urgym_motor_set_state(urgym_motor_t *h, int field, const void *src, void *stream);
+int urgym_motor_stats(urgym_motor_t *h, double *out8, int reset);   /* same layout as urgym_stats */
+int64_t urgym_motor_launch_count(const urgym_motor_t *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,5 +10,6 @@ from .sharding import allreduce_stats, shard_range, summarize  # noqa: F401
 from .sb3_vec_env import SB3VecEnvAdapter  # noqa: F401
 from .vec_env import UR5VecEnv  # noqa: F401
 from .rollout import DeviceReplayRing, Rollout, mlp_policy  # noqa: F401
+from .motor_env import MotorTaskEnv, UR5MotorVecEnv  # noqa: F401
 
 register_with_gymnasium()

@@ -27,7 +27,11 @@ STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions",
 EXPORTS = ["urgym_step_range", "urgym_create", "urgym_destroy", "urgym_last_error", "urgym_obs_dim", "urgym_goal_dim", "urgym_num_envs",
            "urgym_step", "urgym_reset", "urgym_observe", "urgym_refresh", "urgym_get_state", "urgym_set_state",
            "urgym_stats", "urgym_step_host", "urgym_reset_host", "urgym_step_host_async", "urgym_host_wait", "urgym_replay_write", "urgym_set_autoreset", "urgym_get_event",
-           "urgym_set_event", "urgym_set_seed", "urgym_set_link_dist_mode", "urgym_sync_events", "urgym_launch_count", "urgym_profile_enable", "urgym_profile_read"]
+           "urgym_set_event", "urgym_set_seed", "urgym_set_link_dist_mode", "urgym_sync_events", "urgym_launch_count", "urgym_profile_enable", "urgym_profile_read",
+           "urgym_motor_create", "urgym_motor_destroy", "urgym_motor_last_error", "urgym_motor_reset", "urgym_motor_step",
+           "urgym_motor_get_state", "urgym_motor_set_state", "urgym_motor_stats", "urgym_motor_launch_count"]
+MOTOR_F_Q, MOTOR_F_QD, MOTOR_F_GOAL, MOTOR_F_ELAPSED = range(4)
+MOTOR_ENV_ID = "UR5IAIReach-v1"
 
 
 class UrgymError(RuntimeError):
@@ -72,8 +76,23 @@ def lib():
         L.urgym_launch_count.argtypes = [vp]; L.urgym_launch_count.restype = i64
         L.urgym_profile_enable.argtypes = [vp, i32]
         L.urgym_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
+        L.urgym_motor_create.argtypes = [ctypes.POINTER(vp), i64, i64, u64, i32]
+        L.urgym_motor_destroy.argtypes = [vp]
+        L.urgym_motor_last_error.argtypes = [vp]; L.urgym_motor_last_error.restype = ctypes.c_char_p
+        L.urgym_motor_reset.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.urgym_motor_step.argtypes = [vp] + [vp] * 9 + [vp]
+        L.urgym_motor_get_state.argtypes = [vp, i32, vp, vp]
+        L.urgym_motor_set_state.argtypes = [vp, i32, vp, vp]
+        L.urgym_motor_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double), i32]
+        L.urgym_motor_launch_count.argtypes = [vp]; L.urgym_motor_launch_count.restype = i64
         _lib = L
     return _lib
+
+
+def check_motor(handle, rc):
+    if rc != 0:
+        msg = lib().urgym_motor_last_error(handle)
+        raise UrgymError(f"urgym motor error {rc}: {msg.decode() if msg else '?'}")
 
 
 def check(handle, rc):

@@ -236,8 +236,11 @@ ENV_IDS = tuple(nat.TASK_IDS)
 
 def make(env_id: str, render: bool = False, **kwargs) -> RobotTaskEnv:
     """gymnasium.make(id, render=...) for the four reach tasks (UR_gym/__init__.py:19-42)."""
+    if env_id == nat.MOTOR_ENV_ID:           # the motor-driven robot path (UR_gym/__init__.py:7-11, ur_tasks.py:10-21)
+        from .motor_env import MotorTaskEnv
+        return MotorTaskEnv(env_id, render=render, **kwargs)
     if env_id not in nat.TASK_IDS:
-        raise ValueError(f"unknown env id {env_id!r}; known: {ENV_IDS}")
+        raise ValueError(f"unknown env id {env_id!r}; known: {list(ENV_IDS) + [nat.MOTOR_ENV_ID]}")
     return RobotTaskEnv(env_id, render=render, **kwargs)
 
 
