@@ -173,18 +173,19 @@ __device__ __forceinline__ void motor_substeps(const MotorConst &M, float *q, fl
             for (int k = 0; k < 6; k++) a = fmaf(-Minv[i][k], tau[k], a);
             v[i] = fmaf(MOTOR_DT, a, qd[i]);
         }
-        float want[6], lam[6];
+        float want[6], lam[6], idiag[6];
 #pragma unroll
         for (int i = 0; i < 6; i++) {
             want[i] = MOTOR_KP * (target[i] - q[i]) / MOTOR_DT + v[i] + MOTOR_KD * (0.0f - v[i]);
             lam[i] = 0.0f;
+            idiag[i] = 1.0f / Minv[i][i];       // effective mass of the row
         }
 #pragma unroll 1
         for (int it = 0; it < MOTOR_ITERS; it++) {
 #pragma unroll
             for (int i = 0; i < 6; i++) {
                 const float lim = M.force[i] * MOTOR_DT;
-                float l1 = lam[i] + (want[i] - v[i]) / Minv[i][i];
+                float l1 = fmaf(want[i] - v[i], idiag[i], lam[i]);
                 l1 = fminf(fmaxf(l1, -lim), lim);
                 const float dl = l1 - lam[i];
                 lam[i] = l1;
