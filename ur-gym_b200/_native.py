@@ -76,15 +76,19 @@ def lib():
         L.urgym_launch_count.argtypes = [vp]; L.urgym_launch_count.restype = i64
         L.urgym_profile_enable.argtypes = [vp, i32]
         L.urgym_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
-        L.urgym_motor_create.argtypes = [ctypes.POINTER(vp), i64, i64, u64, i32]
-        L.urgym_motor_destroy.argtypes = [vp]
-        L.urgym_motor_last_error.argtypes = [vp]; L.urgym_motor_last_error.restype = ctypes.c_char_p
-        L.urgym_motor_reset.argtypes = [vp, vp, vp, vp, vp, vp]
-        L.urgym_motor_step.argtypes = [vp] + [vp] * 9 + [vp]
-        L.urgym_motor_get_state.argtypes = [vp, i32, vp, vp]
-        L.urgym_motor_set_state.argtypes = [vp, i32, vp, vp]
-        L.urgym_motor_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double), i32]
-        L.urgym_motor_launch_count.argtypes = [vp]; L.urgym_motor_launch_count.restype = i64
+        try:
+            L.urgym_motor_create.argtypes = [ctypes.POINTER(vp), i64, i64, u64, i32]
+            L.urgym_motor_destroy.argtypes = [vp]
+            L.urgym_motor_last_error.argtypes = [vp]; L.urgym_motor_last_error.restype = ctypes.c_char_p
+            L.urgym_motor_reset.argtypes = [vp, vp, vp, vp, vp, vp]
+            L.urgym_motor_step.argtypes = [vp] + [vp] * 9 + [vp]
+            L.urgym_motor_get_state.argtypes = [vp, i32, vp, vp]
+            L.urgym_motor_set_state.argtypes = [vp, i32, vp, vp]
+            L.urgym_motor_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double), i32]
+            L.urgym_motor_launch_count.argtypes = [vp]; L.urgym_motor_launch_count.restype = i64
+        except AttributeError:
+            if not os.environ.get("URGYM_B200_LIB"):      # only an A/B build of an older revision may lack the motor entry points
+                raise
         _lib = L
     return _lib
 

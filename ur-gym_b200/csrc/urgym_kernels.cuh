@@ -353,13 +353,15 @@ __global__ void __launch_bounds__(Blk<GEOM>::STEP, Blk<GEOM>::STEP_MINBLOCKS) ur
 
     const int64_t wbase = (int64_t)blockIdx.x * B + warp * W;                 // first env of this warp
     if (!HULL && wbase >= A.n) return;                       // (hull geometry: every warp of the block takes part in its barriers)
-    const int rows = wbase >= A.n ? 0 : ((A.n - wbase) < W ? (int)(A.n - wbase) : W);
+    // (the capsule kernels keep the plain expressions: the extra selects of the hull form cost UR5StaReach 9 % -- ptxas
+    // schedules the whole kernel differently around them)
+    const int rows = HULL ? (wbase >= A.n ? 0 : ((A.n - wbase) < W ? (int)(A.n - wbase) : W)) : ((A.n - wbase) < W ? (int)(A.n - wbase) : W);
     float *s_obs = s_tiles + warp * W * TF;
     float *s_scr = s_obs + lane;                              // capsule scratch: column `lane` of a [41][32] block
 
     // every lane runs the step (warp-level barriers inside); lanes past the end redo the last env and store nothing
     const bool live = lane < rows;
-    const int64_t i = live ? wbase + lane : (rows ? wbase + rows - 1 : A.n - 1);
+    const int64_t i = HULL ? (live ? wbase + lane : (rows ? wbase + rows - 1 : A.n - 1)) : wbase + (live ? lane : rows - 1);
     EnvState s;
     StepOut o;
     float vel[6], act[6];

@@ -280,6 +280,7 @@ __global__ void urgym_motor_bump_kernel(uint32_t *event) { event[0] += 1u; }
 __global__ void __launch_bounds__(128) urgym_motor_step_kernel(const __grid_constant__ MotorConst M, const MotorArgs A) {
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= A.n) return;
+    if (threadIdx.x == 0) atomicAdd(A.stats + 6, (unsigned long long)min((int64_t)128, A.n - i));      // env steps
     float q[6], qd[6], target[6], goal[3];
 #pragma unroll
     for (int k = 0; k < 6; k++) { q[k] = A.st.q[k][i]; qd[k] = A.st.qd[k][i]; }
