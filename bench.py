@@ -132,7 +132,7 @@ def run_reference(args, rank, world):
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.pause = index, [], set(), False, None, False
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -151,6 +151,9 @@ class ClockSampler(threading.Thread):
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
         while not self.stop_flag:
+            if self.pause:
+                time.sleep(0.001)
+                continue
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -257,6 +260,20 @@ def measure_device(ug, torch, dist, dev, local_rank, rank, world, task, n, geome
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
     st = env.stats(reset=True)                       # episodes finished inside the timed region only
+    # per-kernel durations, right after the timed region (same clocks: the 0.25 s sampling repeat below would drop a
+    # power-capped GPU to its sustained clock first): CUDA events recorded by the library on the launching stream directly around each kernel
+    # (urgym_profile_enable), over back-to-back eager steps (one chain, serial kernels)
+    ks = max(8, min(64, steps))
+    sampler.pause = True                             # clocks are sampled over the timed region (and its repeat), not here
+    env.L.urgym_profile_enable(env.h, 1)
+    for k in range(ks):
+        env.step(ring[k % 8])
+    a_ms, b_ms, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    env.L.urgym_profile_read(env.h, ctypes.byref(a_ms), ctypes.byref(b_ms), ctypes.byref(cnt))
+    env.L.urgym_profile_enable(env.h, 0)
+    env.stats(reset=True)
+    torch.cuda.synchronize(dev)
+    sampler.pause = False
     clock_note = "sampled during the timed region (NVML, 5 ms period)"
     if len(sampler.samples) < 8:
         t_end = time.perf_counter() + 0.25           # too short for the 5 ms sampler: an untimed repeat of the same loop
@@ -272,16 +289,6 @@ def measure_device(ug, torch, dist, dev, local_rank, rank, world, task, n, geome
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         st = ug.allreduce_stats(st, device=dev)
     ms_max = float(t.item())
-    # per-kernel durations: CUDA events recorded by the library on the launching stream directly around each kernel
-    # (urgym_profile_enable), over back-to-back eager steps (one chain, serial kernels)
-    ks = max(8, min(64, steps))
-    env.L.urgym_profile_enable(env.h, 1)
-    for k in range(ks):
-        env.step(ring[k % 8])
-    a_ms, b_ms, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
-    env.L.urgym_profile_read(env.h, ctypes.byref(a_ms), ctypes.byref(b_ms), ctypes.byref(cnt))
-    env.L.urgym_profile_enable(env.h, 0)
-    env.stats(reset=True)
     return dict(env=env, ring=ring, ms=ms, ms_max=ms_max, steps=steps, stats=st, chains=chains, graph_steps=gs,
                 kernel_ms=a_ms.value, reset_kernel_ms=b_ms.value, clocks=dict(sampler.result(), how=clock_note),
                 value=n * world * steps / (ms_max * 1e-3), launches=2 * steps * chains + (steps // gs + (1 if rem else 0)) * (chains > 1))

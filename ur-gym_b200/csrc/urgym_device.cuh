@@ -52,7 +52,16 @@ URGYM_HD void sincos_fast(float x, float *s, float *c) {
     sincosf(x, s, c);
 #endif
 }
-// atan2 with 3e-7 absolute accuracy in ~25 instructions (libdevice's is ~55 and is called 8 times per env step):
+// the same for an argument known to lie in [-pi, pi] (half Euler angles, half rotation angles): no reduction
+URGYM_HD void sincos_small(float x, float *s, float *c) {
+#ifdef __CUDA_ARCH__
+    *s = __sinf(x);
+    *c = __cosf(x);
+#else
+    sincosf(x, s, c);
+#endif
+}
+// atan2 with 4e-7 absolute accuracy in ~23 instructions (libdevice's is ~55 and is called 7 times per env step):
 // reduce to t = min(|x|,|y|)/max(|x|,|y|) in [0,1], minimax odd polynomial for atan(t), undo the reductions.
 // The host instantiation uses libm.
 URGYM_HD float atan2_inl(float y, float x) {
@@ -61,17 +70,16 @@ URGYM_HD float atan2_inl(float y, float x) {
     float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
     float t = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
     float t2 = t * t;
-    // atan(t)/t on [0,1] as a degree-8 polynomial in t^2 (Chebyshev fit, max abs error of atan 3.6e-8 before rounding;
-    // 2.7e-7 for the whole function evaluated in FP32 over 2e6 random arguments)
-    float p = 0.0028340642f;
-    p = fmaf(p, t2, -0.01600503f);
-    p = fmaf(p, t2, 0.042587608f);
-    p = fmaf(p, t2, -0.07495446f);
-    p = fmaf(p, t2, 0.10636754f);
-    p = fmaf(p, t2, -0.14202571f);
-    p = fmaf(p, t2, 0.19992484f);
-    p = fmaf(p, t2, -0.33333066f);
-    p = fmaf(p, t2, 1.0f);
+    // atan(t)/t on [0,1] as a degree-6 polynomial in t^2 (weighted minimax fit: max abs error of atan 2.5e-7 in exact
+    // arithmetic, 3.4e-7 evaluated in FP32; two more terms buy nothing in FP32 -- 1.2e-7 -- and cost two dependent FMAs
+    // in each of the seven atan2 of a step)
+    float p = 0.0068117789924144745f;
+    p = fmaf(p, t2, -0.03360418975353241f);
+    p = fmaf(p, t2, 0.07962365448474884f);
+    p = fmaf(p, t2, -0.1323334276676178f);
+    p = fmaf(p, t2, 0.19807817041873932f);
+    p = fmaf(p, t2, -0.3331736922264099f);
+    p = fmaf(p, t2, 0.9999961256980896f);
     float r = p * t;
     if (ay > ax) r = 1.57079637f - r;
     if (x < 0.0f) r = 3.14159274f - r;
@@ -307,11 +315,19 @@ URGYM_HD void mat_from_quat(Quat q, float *R) {
 
 // scipy Rotation.from_euler('ZYX', e).as_quat(): R = Rz(e0)Ry(e1)Rx(e2)   utils.py:48-54 (quirk Q2: e is PyBullet's
 // (roll,pitch,yaw), so roll is used as the z angle -- replicated literally)
+// SMALL: the angles are Euler angles that came out of atan2 (|e| <= pi): no range reduction
+template <bool SMALL = false>
 URGYM_HD Quat quat_ZYX(float e0, float e1, float e2) {
     float sz, cz, sy, cy, sx, cx;
-    sincos_fast(0.5f * e0, &sz, &cz);
-    sincos_fast(0.5f * e1, &sy, &cy);
-    sincos_fast(0.5f * e2, &sx, &cx);
+    if (SMALL) {
+        sincos_small(0.5f * e0, &sz, &cz);
+        sincos_small(0.5f * e1, &sy, &cy);
+        sincos_small(0.5f * e2, &sx, &cx);
+    } else {
+        sincos_fast(0.5f * e0, &sz, &cz);
+        sincos_fast(0.5f * e1, &sy, &cy);
+        sincos_fast(0.5f * e2, &sx, &cx);
+    }
     Quat q;
     q.x = cz * cy * sx - sz * sy * cx;
     q.y = cz * sy * cx + sz * cy * sx;

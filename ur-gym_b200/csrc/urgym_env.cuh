@@ -231,7 +231,7 @@ template <int TASK> URGYM_HD ObstW obstacle_cached(const float *E, const float *
         const float wn2 = dot(w, w);
         const float inv = wn2 > 0.0f ? rsqrt_f(wn2) : 0.0f;
         float sn, cs;
-        sincos_fast(0.5f * t * (wn2 * inv), &sn, &cs);
+        sincos_small(0.5f * t * (wn2 * inv), &sn, &cs);      // t |w| <= the angle between two orientations <= pi
         const float k = sn * inv;
         Quat r; r.x = w.x * k; r.y = w.y * k; r.z = w.z * k; r.w = cs;
         Quat qs; qs.x = C[4]; qs.y = C[5]; qs.z = C[6]; qs.w = C[7];
@@ -246,7 +246,8 @@ template <int TASK> URGYM_HD ObstW obstacle_cached(const float *E, const float *
 // exact squared distance between segment ab and the axis-aligned box (c, he).  g(t) = 1/2 d/dt dist^2 is monotone
 // and piecewise linear with breakpoints where the point crosses a slab face; bracket the root between breakpoints.
 // (out of line: it runs only for links that come close to the table or the track)
-static URGYM_OOL float seg_box_dist2(float3 a, float3 b, float3 c, float3 he) {
+template <bool ROLLED>
+static URGYM_OOL float seg_box_dist2_t(float3 a, float3 b, float3 c, float3 he) {
     float3 p0 = a - c, d = b - a;
     auto ex = [](float p, float h) { return p - clampf(p, -h, h); };
     auto g = [&](float t) {
@@ -259,24 +260,27 @@ static URGYM_OOL float seg_box_dist2(float3 a, float3 b, float3 c, float3 he) {
     float lo = 0.0f, hi = 1.0f, glo = g(0.0f), ghi = g(1.0f);
     if (glo >= 0.0f) return d2(0.0f);
     if (ghi <= 0.0f) return d2(1.0f);
-    const float pp[3] = {p0.x, p0.y, p0.z}, dd[3] = {d.x, d.y, d.z}, hh[3] = {he.x, he.y, he.z};
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        if (dd[i] != 0.0f) {
-            float inv = fdiv(1.0f, dd[i]);
-#pragma unroll
-            for (int sgn = 0; sgn < 2; sgn++) {
-                float t = ((sgn ? hh[i] : -hh[i]) - pp[i]) * inv;
-                if (t > lo && t < hi) {
-                    float gt = g(t);
-                    if (gt < 0.0f) { lo = t; glo = gt; } else { hi = t; ghi = gt; }
-                }
+    // The six slab-face crossings.  ROLLED: a rolled loop -- the routine runs for one or two lanes of a warp, and unrolled its
+    // 250 instructions pushed the UR5StaReach / UR5DynReach step kernels past the 32 KB instruction cache (DESIGN.md section
+    // 5: misses 582 k -> 133 k per launch, Sta -3.3 %, Dyn -1.3 %); the smaller UR5OriReach / UR5ObsReach kernels keep the
+    // unrolled form (its dependent chain is shorter: +1 % rolled).
+#pragma unroll (ROLLED ? 1 : 6)
+    for (int k = 0; k < 6; k++) {
+        const int i = k >> 1;
+        const float pi = i == 0 ? p0.x : (i == 1 ? p0.y : p0.z), di = i == 0 ? d.x : (i == 1 ? d.y : d.z);
+        const float hi_ = i == 0 ? he.x : (i == 1 ? he.y : he.z);
+        if (di != 0.0f) {
+            const float t = (((k & 1) ? hi_ : -hi_) - pi) * fdiv(1.0f, di);
+            if (t > lo && t < hi) {
+                const float gt = g(t);
+                if (gt < 0.0f) { lo = t; glo = gt; } else { hi = t; ghi = gt; }
             }
         }
     }
     float t = (ghi > glo) ? lo + (hi - lo) * fdiv(-glo, ghi - glo) : lo;
     return d2(t);
 }
+static URGYM_OOL float seg_box_dist2(float3 a, float3 b, float3 c, float3 he) { return seg_box_dist2_t<true>(a, b, c, he); }
 URGYM_HD float point_seg_dist2(float3 p, float3 a, float3 b) {
     float3 ab = b - a, ap = p - a;
     float den = dot(ab, ab);
@@ -302,8 +306,7 @@ template <> struct LinkShape<GEOM_CAPSULE> {
     }
     // getClosestPoints(UR5, obstacle, linkIndexA=l)[0][8], capsule geometry                 pyb_setup.py:439-456
     URGYM_HD float obstacle_dist(const ModelConst &M, int l, const ObstW &O) const {
-        float3 oa = O.c - M.fit_obst_h * O.u, ob = O.c + M.fit_obst_h * O.u;
-        return sqrtf(segseg_dist2(a, b, oa, ob)) - M.fit_obst[l];
+        return sqrtf(seg_axis_dist2(a, b, O.c, O.u, M.fit_obst_h, M.cap_ia[l])) - M.fit_obst[l];     // as in robot_pass_capsule
     }
     // getClosestPoints(UR5, table | track, linkIndexA=l)[0][8], capsule geometry (link-distance mode "workbench")
     URGYM_HD float box_dist(const ModelConst &M, int l, int box) const {
@@ -593,7 +596,8 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
         const float pr = fminf(fminf(point_box_dist2(a, bc, bh), point_box_dist2(b, bc, bh)), point_box_dist2(0.5f * (a + b), bc, bh));
         if (pr <= reach * reach) { hit = true; continue; }
 #endif
-        hit = hit || (sqrtf(seg_box_dist2(a, b, bc, bh)) - M.fit_box[l] - M.box_margin[box] <= URGYM_COLLISION_MARGIN);
+        constexpr bool ROLLED = TASK == TASK_STA || TASK == TASK_DYN;
+        hit = hit || (sqrtf(seg_box_dist2_t<ROLLED>(a, b, bc, bh)) - M.fit_box[l] - M.box_margin[box] <= URGYM_COLLISION_MARGIN);
     }
     // self pairs (1:3,4,5,6) (2:4,5,6) (3:5,6), pair index p = 0..8 in that order: a broad phase for all nine with static
     // indices, then the exact segment-segment test only for the pairs it leaves, in a rolled loop.
@@ -697,7 +701,7 @@ URGYM_HD bool goal_metrics(const float *ee, const float *E, const float *C, floa
     ang = 0.0f;
     if (Traits<TASK>::ORI) {
         Quat g; g.x = C[0]; g.y = C[1]; g.z = C[2]; g.w = C[3];
-        ang = angular_distance(quat_ZYX(ee[3], ee[4], ee[5]), g);
+        ang = angular_distance(quat_ZYX<true>(ee[3], ee[4], ee[5]), g);        // ee[3..5] come out of atan2
         ok = ok && (ang < 0.0873f);
     }
     return ok;

@@ -32,7 +32,7 @@ using namespace urgym;
 #endif
 #define URGYM_MAX_CHAINS 8     /* independent step chains (env sub-ranges advanced on their own streams) */
 #ifndef URGYM_STEP_MINBLOCKS
-#define URGYM_STEP_MINBLOCKS (768 / URGYM_STEP_BLOCK)   /* 24 resident step-kernel warps per SM: the register allocation is held to 80 */
+#define URGYM_STEP_MINBLOCKS (736 / URGYM_STEP_BLOCK)   /* 23 resident step-kernel warps per SM, 88 registers (24 warps at 80: +0.3 %; 22: +0.1 %; 20, 26: +2.5 %) */
 #endif
 #define URGYM_STAT_SLOTS 64
 #define URGYM_RETURN_SCALE 65536.0f     /* episode returns are summed in 2^-16 fixed point: order-independent */
@@ -479,7 +479,7 @@ struct AuxArgs {
 
 // RobotTaskEnv.reset (core.py:263-273) of `cnt` envs listed in s_list (indices relative to gbase), by one warp, 32 at a
 // time with one env per lane.  ReachDyn's rejection loop accepts only ~17.5 % of its draws on the cheap start-end
-// distance rule, so that part of the search runs 4 iterations per env in parallel (4-lane groups, 8 envs per pass)
+// distance rule, so that part of the search runs 8 iterations per env in parallel (8-lane groups, 4 envs per pass)
 // before the lane-per-env phase evaluates the surviving iteration completely.  Returns this lane's share of the
 // rejection iterations used.
 template <int TASK, int GEOM>
@@ -505,26 +505,44 @@ __device__ __forceinline__ unsigned long long reset_listed(const ModelConst &c_m
     for (int j = lane; j < cnt; j += W) s_k[j] = 0;
     __syncwarp();
     if (TT::DYN) {
-        const int sub = lane & 3, grp = lane >> 2;
-        for (int j0 = 0; j0 < cnt; j0 += 8) {
-            const int j = j0 + grp;
+        // The 32 lanes test 32 (env, iteration) candidates per round, dealt out over the envs that are still searching: with u
+        // of them left, env number r (in lane order) gets the lanes r, r + u, r + 2u, ... and tests its next iterations
+        // there; the smallest passing one wins, an env without one moves its window on.  ~183 candidates are needed for
+        // 32 envs (acceptance 17.5 %), so a batch takes ~8 rounds; fixed groups of 4 or 8 lanes per env took 16.2 / 12.9,
+        // because every pass waited for its unluckiest env.
+        for (int jb = 0; jb < cnt; jb += W) {
+            const int j = jb + lane;
             const bool have = j < cnt;
-            ResetStream rs;
-            rs.key = A.key; rs.episode = event; rs.bpi = TT::BPI; rs.iter = 0; rs.env_lo = rs.env_hi = 0;
-            if (have) {
-                const uint64_t genv = (uint64_t)(A.offset + gbase + s_list[j]);
-                rs.env_lo = (uint32_t)genv; rs.env_hi = (uint32_t)(genv >> 32);
-            }
+            const uint64_t genv = have ? (uint64_t)(A.offset + gbase + s_list[j]) : 0ull;
+            const uint32_t my_lo = (uint32_t)genv, my_hi = (uint32_t)(genv >> 32);
             bool found = !have;
-            int kstar = 0;
-            for (int k0 = 0; k0 < URGYM_MAX_RESET_ITERS; k0 += 4) {
-                bool ok = false;
-                if (!found) { rs.iter = (uint32_t)(k0 + sub); ok = dyn_pair_far_enough(rs); }
-                const unsigned gm = (__ballot_sync(0xffffffffu, ok) >> (grp * 4)) & 0xFu;
-                if (!found && gm) { found = true; kstar = k0 + __ffs(gm) - 1; }
-                if (__all_sync(0xffffffffu, found)) break;
+            int next_k = 0, kstar = URGYM_MAX_RESET_ITERS - 1;
+            for (;;) {
+                const unsigned U = __ballot_sync(0xffffffffu, !found);
+                if (U == 0u) break;
+                const int u = __popc(U);
+                const int r = lane % u, m = lane / u;
+                const int src = (int)__fns(U, 0u, r + 1);               // lane of the r-th env still searching
+                ResetStream rs;
+                rs.key = A.key; rs.episode = event; rs.bpi = TT::BPI;
+                rs.env_lo = __shfl_sync(0xffffffffu, my_lo, src); rs.env_hi = __shfl_sync(0xffffffffu, my_hi, src);
+                const int it = __shfl_sync(0xffffffffu, next_k, src) + m;
+                rs.iter = (uint32_t)it;
+                const bool ok = it < URGYM_MAX_RESET_ITERS && dyn_pair_far_enough(rs);
+                const unsigned B = __ballot_sync(0xffffffffu, ok);
+                if (!found) {
+                    const int mine = __popc(U & ((1u << lane) - 1u));      // this env's number among the searching ones
+                    int tested = 0;
+                    for (int t = mine; t < W; t += u, tested++) {
+                        if ((B >> t) & 1u) { found = true; kstar = next_k + tested; break; }
+                    }
+                    if (!found) {
+                        next_k += tested;
+                        if (next_k >= URGYM_MAX_RESET_ITERS) found = true;      // give up: kstar = the last iteration
+                    }
+                }
             }
-            if (have && sub == 0) s_k[j] = found ? kstar : URGYM_MAX_RESET_ITERS - 1;
+            if (have) s_k[j] = kstar;
         }
         __syncwarp();
     }
