@@ -45,12 +45,21 @@ def test_no_cpu_fallback():
     h = ctypes.c_void_p()
     assert L.urgym_create(ctypes.byref(h), 0, 1, 4, 0, 0, 0) == -2          # URGYM_ENODEVICE
     assert b"no CPU path" in L.urgym_last_error(None)
+    # the motor-driven env has no CPU path either
+    with pytest.raises(ug.UrgymError):
+        ug.UR5MotorVecEnv(4)
+    with pytest.raises(ug.UrgymError):
+        ug.make("UR5IAIReach-v1")
+    assert L.urgym_motor_create(ctypes.byref(h), 4, 0, ctypes.c_uint64(0), 0) == -2   # URGYM_ENODEVICE
+    assert b"no CPU path" in L.urgym_motor_last_error(None)
+    with pytest.raises(ValueError):
+        ug.make("UR5RegReach-v1")                      # not built
 
 
 def test_product_never_imports_the_oracle():
     """no import / include / dlopen of anything under oracle/ from the product (comments may name the calibration tool)"""
     pkg = os.path.join(ROOT, "ur-gym_b200")
-    pat = re.compile(r"(^|\s)(from|import)\s+oracle\b|#\s*include\s+\"[^\"]*oracle|libur_oracle|oracle_env", re.M)
+    pat = re.compile(r"(^|\s)(from|import)\s+oracle\b|#\s*include\s+\"[^\"]*oracle|libur_oracle|libur_motor_oracle|oracle_env|import\s+motor_oracle", re.M)
     for dp, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")) and "build" not in dp:
