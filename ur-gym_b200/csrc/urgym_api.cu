@@ -361,6 +361,7 @@ static int step_range(urgym_env *h, int64_t first, int64_t count, int bump, int 
         memset(&R, 0, sizeof(R));
         R.st = A.st; R.n = count; R.offset = h->offset + first; R.key = key_of(h->seed);
         R.queue = A.queue; R.qcount = A.qcount; R.autoreset = 1;
+        R.f_term = A.term; R.f_trunc = A.trunc; R.f_succ = A.succ;
         R.obs = A.obs; R.ach = A.ach; R.des = A.des;
         // (the step kernel has already written the terminal rows)
         R.stats = h->stats; R.event = h->d_event; R.chain = chain; R.hull = h->hull;
