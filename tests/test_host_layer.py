@@ -52,8 +52,10 @@ def test_no_cpu_fallback():
         ug.make("UR5IAIReach-v1")
     assert L.urgym_motor_create(ctypes.byref(h), 4, 0, ctypes.c_uint64(0), 0) == -2   # URGYM_ENODEVICE
     assert b"no CPU path" in L.urgym_motor_last_error(None)
+    with pytest.raises(NotImplementedError, match="IndexError"):
+        ug.make("UR5RegReach-v1")                      # the reference's env cannot step
     with pytest.raises(ValueError):
-        ug.make("UR5RegReach-v1")                      # not built
+        ug.make("UR5NoSuchReach-v1")
 
 
 def test_product_never_imports_the_oracle():

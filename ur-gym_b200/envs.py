@@ -239,6 +239,12 @@ def make(env_id: str, render: bool = False, **kwargs) -> RobotTaskEnv:
     if env_id == nat.MOTOR_ENV_ID:           # the motor-driven robot path (UR_gym/__init__.py:7-11, ur_tasks.py:10-21)
         from .motor_env import MotorTaskEnv
         return MotorTaskEnv(env_id, render=render, **kwargs)
+    if env_id == "UR5RegReach-v1":
+        # The reference registers this id (UR_gym/__init__.py:13-17) but its env cannot take a step: its scene has five
+        # bodies (UR5, plane, table, track, target; reach.py:92-103) and PyBullet.check_collision reads keys[5]
+        # (pyb_setup.py:398-399) -> IndexError at the first env.step().  There is no behaviour to reproduce.
+        raise NotImplementedError("UR5RegReach-v1: the reference's own env raises IndexError at its first step "
+                                  "(pyb_setup.py:398-399 reads keys[5] of a five-body scene); not built, see DESIGN.md section 8")
     if env_id not in nat.TASK_IDS:
         raise ValueError(f"unknown env id {env_id!r}; known: {list(ENV_IDS) + [nat.MOTOR_ENV_ID]}")
     return RobotTaskEnv(env_id, render=render, **kwargs)
