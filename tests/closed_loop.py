@@ -74,6 +74,52 @@ def grid_positions(low, high, repeat=5):
     return np.array(pts, np.float32)
 
 
+GRID_LOW = {"UR5OriReach-v1": [0.3, -0.5, 0.0], "UR5DynReach-v1": [0.4, -0.5, 0.0]}     # reach.py:151,584
+GRID_HIGH = [0.75, 0.5, 0.2]
+
+
+def axis_profiles(pos, success, steps):
+    """The spatial profile of a grid run, as tests/golden/make_policy_fixtures.py extracts it from the published per-episode
+    lines: per grid value of each goal-position axis, mean step count of the successes, failures, episodes."""
+    pos, success, steps = np.asarray(pos, np.float64), np.asarray(success, bool), np.asarray(steps)
+    out = {}
+    for ax in range(3):
+        cell = np.rint(pos[:, ax] * 20).astype(int)
+        vals = np.unique(cell)
+        out[f"axis{ax}_values"] = (vals / 20).tolist()
+        out[f"axis{ax}_success_steps"] = [float(steps[success & (cell == v)].mean()) for v in vals]
+        out[f"axis{ax}_success_steps_sd"] = [float(steps[success & (cell == v)].std()) for v in vals]
+        out[f"axis{ax}_failures"] = [int((~success & (cell == v)).sum()) for v in vals]
+        out[f"axis{ax}_episodes"] = [int((cell == v).sum()) for v in vals]
+    return out
+
+
+def compare_profiles(r, z_max=4.0, mean_step_tol=0.15):
+    """The run's spatial profile against the published one.  Per grid value of every axis (250-1750 episodes each): the
+    difference of the mean step counts of the successes in units of its standard error (sd of the step counts measured in
+    this run, both sides), and the difference of the failure shares in units of the binomial standard error at the pooled
+    share.  Asserts every |z| <= z_max, the mean absolute step difference over all grid values <= mean_step_tol, and a
+    correlation >= 0.98 between the two x profiles (the steps a goal needs grow as it comes closer to the base: 5.4 -> 8.3).
+    Returns (worst step z, worst failure z, mean |step difference|, correlation)."""
+    pub, prof = r["published"], r["axis_profiles"]
+    zs, zf, diffs = 0.0, 0.0, []
+    for ax in range(3):
+        assert np.allclose(pub[f"published_axis{ax}_values"], prof[f"axis{ax}_values"], atol=1e-6), (ax, prof[f"axis{ax}_values"])
+        assert np.array_equal(pub[f"published_axis{ax}_episodes"], prof[f"axis{ax}_episodes"]), ax
+        n = np.asarray(prof[f"axis{ax}_episodes"], float)
+        a = np.asarray(pub[f"published_axis{ax}_success_steps"]); b = np.asarray(prof[f"axis{ax}_success_steps"])
+        fa = np.asarray(pub[f"published_axis{ax}_failures"]) / n; fb = np.asarray(prof[f"axis{ax}_failures"]) / n
+        se_s = np.asarray(prof[f"axis{ax}_success_steps_sd"]) * np.sqrt(2.0 / (n * (1.0 - fb)))
+        pool = np.maximum(0.5 * (fa + fb), 0.01)
+        se_f = np.sqrt(pool * (1.0 - pool) * 2.0 / n)
+        zs = max(zs, float((np.abs(a - b) / se_s).max())); zf = max(zf, float((np.abs(fa - fb) / se_f).max()))
+        diffs += np.abs(a - b).tolist()
+    cx = float(np.corrcoef(pub["published_axis0_success_steps"], prof["axis0_success_steps"])[0, 1])
+    res = (zs, zf, float(np.mean(diffs)), cx)
+    assert zs <= z_max and zf <= z_max and res[2] <= mean_step_tol and cx >= 0.98, (res, prof)
+    return res
+
+
 def dyn_scenarios(goal_pos, seed=0):
     """reach.py:685-700 reset_generate: goal rotation, obstacle start and end re-sampled until accepted"""
     from oracle import oracle_env as oe
@@ -121,8 +167,7 @@ def run(env_id, geometry="capsule", seed=0, device=0, max_envs=None, link_dist=N
     act, pub = load_policy(env_id, dev)
     link_dist = link_dist or POLICY_LINK_DIST[env_id]
     if env_id in ("UR5OriReach-v1", "UR5DynReach-v1"):
-        low = [0.3, -0.5, 0.0] if env_id == "UR5OriReach-v1" else [0.4, -0.5, 0.0]
-        pos = grid_positions(np.array(low), np.array([0.75, 0.5, 0.2]))
+        pos = grid_positions(np.array(GRID_LOW[env_id]), np.array(GRID_HIGH))
         n = len(pos)
     else:
         n = 5000
@@ -160,20 +205,38 @@ def run(env_id, geometry="capsule", seed=0, device=0, max_envs=None, link_dist=N
         collided |= ends & term.bool() & ~info["is_success"].bool()
         steps = torch.where(ends, torch.full_like(steps, t), steps)
         finished |= ends
-    res = taxonomy(success.cpu().numpy(), collided.cpu().numpy(), steps.cpu().numpy(), ret.cpu().numpy(), pub,
-                   {"env_id": env_id, "geometry": geometry, "link_dist": link_dist, "policy_ld_ablation": ld_ablation})
+    extra = {"env_id": env_id, "geometry": geometry, "link_dist": link_dist, "policy_ld_ablation": ld_ablation}
+    if env_id in GRID_LOW and n == len(pos):
+        extra["axis_profiles"] = axis_profiles(pos, success.cpu().numpy(), steps.cpu().numpy())
+    res = taxonomy(success.cpu().numpy(), collided.cpu().numpy(), steps.cpu().numpy(), ret.cpu().numpy(), pub, extra)
     env.close()
     return res
 
 
-def run_host(env_id, geom=1, n=500, seed=0, link_dist_mode=0, ld_ablation=None):
+def run_host(env_id, geom=1, n=500, seed=0, link_dist_mode=0, ld_ablation=None, grid=False):
     """The same protocol on tests/hostcheck (the product's per-env code compiled for the host): the CPU tier's
-    closed-loop check, natural-reset scenarios for every task."""
+    closed-loop check, natural-reset scenarios for every task; grid=True (UR5OriReach, UR5DynReach): the reference's own scenario
+    grid of goal positions (utils/generate.py:23-47,66-86), all of it, with the spatial profile in the result."""
     from tests._hostcheck import HostCheckSim, GOAL_DIM, TASK_ID
     act, pub = load_policy_numpy(env_id)
+    pos = None
+    if grid:
+        assert env_id in GRID_LOW
+        pos = grid_positions(np.array(GRID_LOW[env_id]), np.array(GRID_HIGH))
+        n = len(pos)
     sim = HostCheckSim(env_id, geom, n, seed=seed, autoreset=False, link_dist_mode=link_dist_mode)
     obs = sim.reset()
     G = GOAL_DIM[TASK_ID[env_id]]
+    if grid and env_id == "UR5OriReach-v1":
+        goal = obs[:, 12:12 + G].copy()
+        goal[:, :3] = pos
+        sim.set_goal(goal)
+        obs = sim.observe()
+    elif grid:
+        sc = dyn_scenarios(pos, seed)
+        sim.set_goal(sc[:, :6]); sim.set_obstacle(sc[:, 6:12]); sim.set_obstacle_end(sc[:, 12:])
+        sim.refresh()                           # tail of set_goal_and_obstacle (reach.py:702-713): link_dist, collision
+        obs = sim.observe()
     finished = np.zeros(n, bool); success = np.zeros(n, bool); collided = np.zeros(n, bool)
     steps = np.zeros(n, int); ret = np.zeros(n)
     for t in range(100):
@@ -192,10 +255,12 @@ def run_host(env_id, geom=1, n=500, seed=0, link_dist_mode=0, ld_ablation=None):
         finished |= ends
         if finished.all():
             break
-    return taxonomy(success, collided, steps, ret, pub,
-                    {"env_id": env_id, "geometry": "capsule" if geom == 1 else "hull",
-                     "link_dist": "workbench" if link_dist_mode else "obstacle", "policy_ld_ablation": ld_ablation,
-                     "scenarios": "natural resets (host instantiation)"})
+    extra = {"env_id": env_id, "geometry": "capsule" if geom == 1 else "hull",
+             "link_dist": "workbench" if link_dist_mode else "obstacle", "policy_ld_ablation": ld_ablation,
+             "scenarios": "goal-position grid (host instantiation)" if grid else "natural resets (host instantiation)"}
+    if grid:
+        extra["axis_profiles"] = axis_profiles(pos, success, steps)
+    return taxonomy(success, collided, steps, ret, pub, extra)
 
 
 if __name__ == "__main__":

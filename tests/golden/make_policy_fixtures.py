@@ -22,6 +22,7 @@ import torch
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 STEP_BINS = [0, 3, 5, 7, 9, 12, 16, 25, 50, 100]
+GRID_LOW = {"Ori": [0.3, -0.5, 0.0], "Dyn": [0.4, -0.5, 0.0]}      # ReachOri / ReachDyn goal_range_low (reach.py:154,601)
 RESULT = {"Ori": "best.txt", "Obs": "best.txt", "Sta": "best.txt", "Dyn": "best_modeltest_result.txt"}
 
 for t in ("Ori", "Obs", "Sta", "Dyn"):
@@ -44,6 +45,20 @@ for t in ("Ori", "Obs", "Sta", "Dyn"):
     out["published_success_mean_reward"] = np.float64(rew[ok].mean())
     out["published_success_step_hist"] = np.histogram(st[ok], bins=STEP_BINS)[0].astype(np.int64)
     out["published_collision_mean_steps"] = np.float64(st[(st < 99) & ~ok].mean())
+    # Spatial profile of the published per-episode lines.  For Ori and Dyn the scenario list is a grid of goal positions in a
+    # fixed order (utils/generate.py:30-47,66-86: 0.05 m steps, x outermost, 5 scenarios per grid point), so line n of the
+    # result file belongs to a known goal position: per grid value of each axis, the mean step count of the successful
+    # episodes, the number of failures and the number of episodes.
+    if t in GRID_LOW:
+        low, high = GRID_LOW[t], [0.75, 0.5, 0.2]
+        num = [int((high[i] - low[i]) / 0.05) + 1 for i in range(3)]
+        idx = np.array([[i, j, k] for i in range(num[0]) for j in range(num[1]) for k in range(num[2]) for _ in range(5)])
+        assert len(idx) == len(eps), (t, len(idx), len(eps))
+        for ax in range(3):
+            out[f"published_axis{ax}_values"] = np.array([low[ax] + v / 20 for v in range(num[ax])], np.float64)
+            out[f"published_axis{ax}_success_steps"] = np.array([st[ok & (idx[:, ax] == v)].mean() for v in range(num[ax])])
+            out[f"published_axis{ax}_failures"] = np.array([(~ok & (idx[:, ax] == v)).sum() for v in range(num[ax])], np.int64)
+            out[f"published_axis{ax}_episodes"] = np.array([(idx[:, ax] == v).sum() for v in range(num[ax])], np.int64)
     # when the policy was trained (SB3 `start_time`, ns since the epoch) and with which library versions
     meta = json.loads(z.read("data"))
     out["published_train_start_ns"] = np.int64(meta["start_time"])

@@ -19,3 +19,17 @@ def test_obstacle_only_link_dist_breaks_the_2023_policies():
     assert r["collision_rate_pct"] >= 20.0, r
     z = run_host("UR5ObsReach-v1", geom=1, n=300, link_dist_mode=0, ld_ablation="zero")
     assert z["collision_rate_pct"] <= 12.0 and z["success_rate_pct"] >= r["success_rate_pct"] + 15.0, (r, z)
+
+
+@pytest.mark.parametrize("env_id", ["UR5OriReach-v1", "UR5DynReach-v1"])
+def test_spatial_profile_matches_published(env_id):
+    """Where in the workspace the policy needs how many steps, and where it fails.  The scenario lists of UR5OriReach and
+    UR5DynReach are grids of goal positions in a fixed order (utils/generate.py:23-47,66-86), so every published per-episode
+    line belongs to a known goal position (tests/golden/make_policy_fixtures.py).  All 5 250 / 3 675 scenarios are run; per
+    grid value of x, y and z the mean step count of the successes and the failure share must agree with the PyBullet run
+    within 4 standard errors, 0.15 steps on average, and the x profiles (8.3 -> 5.4 steps from the near to the far edge)
+    must correlate at 0.98: the kinematics, the step size and the success thresholds are right across the workspace."""
+    r = run_host(env_id, geom=1, grid=True)
+    from tests.closed_loop import compare_profiles
+    zs, zf, mean_diff, corr = compare_profiles(r)
+    assert abs(r["success_rate_pct"] - r["published"]["published_success_rate_pct"]) <= 3.0, r

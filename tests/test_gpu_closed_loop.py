@@ -28,6 +28,10 @@ def test_shipped_policy_success_rate_matches_published(env_id):
         # the same step counts: its 2023 reward weights are not the shipped ones (not recoverable from the artefacts)
         assert abs(r["mean_reward"] - pub["published_mean_reward"]) <= 0.1 * abs(pub["published_mean_reward"]), r
         assert abs(r["mean_steps"] - pub["published_mean_steps"]) <= 1.0, r
+    if env_id in ("UR5OriReach-v1", "UR5DynReach-v1"):
+        # the scenario list is a grid of goal positions in a fixed order: the spatial profile of steps and failures
+        from tests.closed_loop import compare_profiles
+        compare_profiles(r)
 
 
 @pytest.mark.parametrize("env_id", ALL)

@@ -582,9 +582,6 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
             if (BOX_IN_LOOP) box_tests(M, l, a, b, hit, slow);
         }
     }
-#ifdef URGYM_HIT_SKIPS
-    if (hit) slow = 0u;     // the flag is an OR: a lane that already has its hit needs no exact test
-#endif
     while (slow) {          // exact segment-box distance for the few (link, box) cases left
         const int k = __ffs_hd(slow) - 1;
         slow &= slow - 1u;
@@ -637,9 +634,6 @@ URGYM_HD bool robot_pass_capsule(const ModelConst &M, const float *q, const Obst
             }
             if (d2 <= M.self_far2[p]) need |= 1u << p;
         }
-#ifdef URGYM_HIT_SKIPS
-        if (hit) need = 0u;
-#endif
         while (need) {
             const int p = __ffs_hd(need) - 1;
             need &= need - 1u;
