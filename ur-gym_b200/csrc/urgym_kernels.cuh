@@ -456,192 +456,6 @@ __global__ void __launch_bounds__(Blk<GEOM>::STEP, Blk<GEOM>::STEP_MINBLOCKS) ur
     }
 }
 
-
-#if defined(URGYM_STEP_TILES) && URGYM_STEP_TILES > 1
-// EXPERIMENT (tools/ab_build.sh NAME - "-DURGYM_STEP_TILES=K -DURGYM_STEP_MINBLOCKS=20"): capsule geometry, K consecutive
-// 32-env tiles per one-warp block.  The inputs of the next tile (actions, joint state, hot words: 4.9 KB for UR5DynReach)
-// are fetched with cp.async into a staging area in shared memory while the current tile is computed, so that only the
-// first tile of a block waits for its loads (13-15 % of a warp's life in the one-tile kernel, SASS-level ncu profile).
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-template <int TASK> struct Stage {
-    static constexpr int NG = HotLayout<TASK>::NG;
-    static constexpr int ACT_OFF = 0, Q_OFF = 768, H_OFF = 768 + 1024, BYTES = 768 + 1024 + NG * 1024;
-};
-template <int TASK> __device__ __forceinline__ void stage_issue(const StepArgs &A, int64_t wbase, char *s_in, int lane) {
-    typedef Stage<TASK> S;
-    const char *ga = reinterpret_cast<const char *>(A.actions + wbase * 6);
-    cp_async16(s_in + S::ACT_OFF + lane * 16, ga + lane * 16);
-    if (lane < 16) cp_async16(s_in + S::ACT_OFF + 512 + lane * 16, ga + 512 + lane * 16);
-    const char *gq = reinterpret_cast<const char *>(A.st.q8 + 2 * wbase);
-    cp_async16(s_in + S::Q_OFF + lane * 16, gq + lane * 16);
-    cp_async16(s_in + S::Q_OFF + 512 + lane * 16, gq + 512 + lane * 16);
-#pragma unroll
-    for (int G = 0; G < S::NG; G++) {
-        const char *gh = reinterpret_cast<const char *>(A.st.h8[G] + 2 * wbase);
-        cp_async16(s_in + S::H_OFF + G * 1024 + lane * 16, gh + lane * 16);
-        cp_async16(s_in + S::H_OFF + G * 1024 + 512 + lane * 16, gh + 512 + lane * 16);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int TASK, int GEOM>
-__global__ void __launch_bounds__(32, URGYM_STEP_MINBLOCKS) urgym_step_kernel_mt(const __grid_constant__ ModelConst c_model, const StepArgs A) {
-    typedef Traits<TASK> TT;
-    typedef HotLayout<TASK> L;
-    constexpr int D = TT::OBS, G = TT::GOAL, W = 32, K = URGYM_STEP_TILES;
-    constexpr int TF = TileFloats<TASK, GEOM>::value;
-    extern __shared__ float4 smem4[];
-    float *s_obs = reinterpret_cast<float *>(smem4);
-    char *s_in = reinterpret_cast<char *>(s_obs + W * TF);
-    const int lane = threadIdx.x;
-    if (blockIdx.x == 0 && lane == 0) {
-        if (A.bump == 1) A.event[A.chain] += 1u;
-        if (A.bump == 2) {
-            uint32_t m = 0u;
-            for (int c = 0; c < URGYM_MAX_CHAINS; c++) m = A.event[c] > m ? A.event[c] : m;
-            for (int c = 0; c < URGYM_MAX_CHAINS; c++) A.event[c] = m + 1u;
-        }
-    }
-    const int64_t ntiles = (A.n + W - 1) / W, t0 = (int64_t)blockIdx.x * K;
-    if (t0 >= ntiles) return;
-    const bool can_stage = aligned16(A.actions);
-    bool staged = can_stage && (A.n - t0 * W) >= W;
-    if (staged) stage_issue<TASK>(A, t0 * W, s_in, lane);
-    float *s_scr = s_obs + lane;
-    // The reply of a tile's queue reservation (one atomicAdd per warp with finished envs) is used one tile later: the
-    // one-tile kernel waits ~700 cycles for it at its very end (3 % of a warp's life).
-    unsigned pend_mask = 0u, pend_base = 0u;
-    int64_t pend_wbase = 0;
-#pragma unroll 1
-    for (int k = 0; k < K; k++) {
-        const int64_t wbase = (t0 + k) * W;
-        if (wbase >= A.n) break;
-        const int rows = (A.n - wbase) < W ? (int)(A.n - wbase) : W;
-        const bool live = lane < rows;
-        const int64_t i = wbase + (live ? lane : rows - 1);
-        EnvState s;
-        StepOut o;
-        float vel[6], act[6];
-        if (staged) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            const float2 *sa = reinterpret_cast<const float2 *>(s_in + Stage<TASK>::ACT_OFF + lane * 24);
-            const float2 a0 = sa[0], a1 = sa[1], a2 = sa[2];
-            act[0] = a0.x; act[1] = a0.y; act[2] = a1.x; act[3] = a1.y; act[4] = a2.x; act[5] = a2.y;
-            const float4 *sq = reinterpret_cast<const float4 *>(s_in + Stage<TASK>::Q_OFF + lane * 32);
-            const float4 a = sq[0], b = sq[1];
-            s.q[0] = a.x; s.q[1] = a.y; s.q[2] = a.z; s.q[3] = a.w; s.q[4] = b.x; s.q[5] = b.y;
-            s.elapsed = __float_as_int(b.z);
-            s.ep_ret = b.w;
-#pragma unroll
-            for (int Gq = 0; Gq < L::NG; Gq++) {
-                const float4 *sh = reinterpret_cast<const float4 *>(s_in + Stage<TASK>::H_OFF + Gq * 1024 + lane * 32);
-                float4 v[2] = {sh[0], sh[1]};
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int w = 8 * Gq + 4 * h;
-                    if (w < L::HW) hot_word<TASK>(s, w) = v[h].x;
-                    if (w + 1 < L::HW) hot_word<TASK>(s, w + 1) = v[h].y;
-                    if (w + 2 < L::HW) hot_word<TASK>(s, w + 2) = v[h].z;
-                    if (w + 3 < L::HW) hot_word<TASK>(s, w + 3) = v[h].w;
-                }
-            }
-            if (TT::HAS_OBST) {       // link_dist = last_dist is needed at the end of the step only: plain loads
-                const float4 l = A.st.ld4[i];
-                s.ld[0] = l.x; s.ld[1] = l.y; s.ld[2] = l.z; s.ld[3] = l.w; s.ld[4] = A.st.ld1[i];
-            } else {
-#pragma unroll
-                for (int q = 0; q < 5; q++) s.ld[q] = 0.0f;
-            }
-            __syncwarp();             // every lane has its words: the staging area is free for the next tile
-        } else {
-            const float *ga = A.actions + i * 6;
-#pragma unroll
-            for (int q = 0; q < 6; q++) act[q] = __ldg(ga + q);
-            load_dyn<TASK>(A.st, i, s);
-            load_hot<TASK>(A.st, i, s);
-        }
-        staged = false;
-        if (k + 1 < K && can_stage && (A.n - (wbase + W)) >= W) {
-            stage_issue<TASK>(A, wbase + W, s_in, lane);
-            staged = true;
-        }
-        env_step<TASK, GEOM>(c_model, s, act, nullptr, s_obs + lane * D, o, vel, s_scr, W);
-        if (live) {
-            store_dyn<TASK>(A.st, i, s);
-            A.rew[i] = o.reward;
-            A.term[i] = o.terminated ? 1 : 0;
-            A.trunc[i] = o.truncated ? 1 : 0;
-            A.succ[i] = o.success ? 1 : 0;
-            unsigned long long *slot = A.stats + (size_t)((t0 + k) % URGYM_STAT_SLOTS) * URGYM_STATS_COUNT;
-            if (!A.queue && (o.terminated || o.truncated)) {
-                stat_add(slot + 0, 1ull);
-                stat_add(slot + 1, (unsigned long long)__float2ll_rn(s.ep_ret * URGYM_RETURN_SCALE));
-                stat_add(slot + 2, (unsigned long long)s.elapsed);
-                if (o.success) stat_add(slot + 3, 1ull);
-                if (o.collision) stat_add(slot + 4, 1ull);
-                if (o.truncated && !o.terminated) stat_add(slot + 5, 1ull);
-            }
-            if (lane == 0) stat_add(slot + 6, (unsigned long long)rows);
-        }
-        const unsigned done_mask = __ballot_sync(0xffffffffu, live && (o.terminated || o.truncated));
-        unsigned qbase = 0u;
-        if (A.queue && done_mask && lane == 0) qbase = atomicAdd(A.qcount, (unsigned)__popc(done_mask));
-        __syncwarp();
-        float *gobs = A.obs + wbase * D;
-        if (rows == W && aligned16(gobs)) {
-            float4 *g4 = reinterpret_cast<float4 *>(gobs);
-            const float4 *s4 = reinterpret_cast<const float4 *>(s_obs);
-#pragma unroll
-            for (int q = 0; q < (W * D / 4 + W - 1) / W; q++)
-                if (q * W + lane < W * D / 4) __stcs(g4 + q * W + lane, s4[q * W + lane]);
-        } else {
-            for (int q = lane; q < rows * D; q += W) gobs[q] = s_obs[q];
-        }
-        if (live) {
-            const float *row = s_obs + lane * D;
-            if (A.ach) {
-                float *g = A.ach + (wbase + lane) * G;
-#pragma unroll
-                for (int q = 0; q < G; q++) g[q] = row[q];
-            }
-            if (A.des) {
-                float *g = A.des + (wbase + lane) * G;
-#pragma unroll
-                for (int q = 0; q < G; q++) g[q] = row[12 + q];
-            }
-        }
-        if (done_mask && (A.tobs || A.tach)) {
-            for (unsigned m = done_mask; m; m &= m - 1u) {
-                const int r = __ffs(m) - 1;
-                const float *row = s_obs + r * D;
-                if (A.tobs) {
-                    float *g = A.tobs + (wbase + r) * D;
-                    if (lane < D) g[lane] = row[lane];
-                    if (lane + W < D) g[lane + W] = row[lane + W];
-                }
-                if (A.tach && lane < G) A.tach[(wbase + r) * G + lane] = row[lane];
-            }
-        }
-        if (pend_mask) {
-            const unsigned pb = __shfl_sync(0xffffffffu, pend_base, 0);
-            if ((pend_mask >> lane) & 1u) A.queue[pb + __popc(pend_mask & ((1u << lane) - 1u))] = (int)(pend_wbase + lane);
-        }
-        pend_mask = A.queue ? done_mask : 0u; pend_base = qbase; pend_wbase = wbase;
-        __syncwarp();                 // the tile in shared memory is rewritten by the next env_step
-    }
-    if (pend_mask) {
-        const unsigned pb = __shfl_sync(0xffffffffu, pend_base, 0);
-        if ((pend_mask >> lane) & 1u) A.queue[pb + __popc(pend_mask & ((1u << lane) - 1u))] = (int)(pend_wbase + lane);
-    }
-}
-template <int TASK, int GEOM> constexpr size_t step_mt_smem_bytes() {
-    return (size_t)32 * TileFloats<TASK, GEOM>::value * sizeof(float) + Stage<TASK>::BYTES;
-}
-#endif
-
 // ------------------------------------------------------------------------------------------------ reset / auto-reset
 struct AuxArgs {
     StateView st;
@@ -1008,13 +822,6 @@ static inline unsigned grid_for(int64_t n) { return (unsigned)((n + URGYM_BLOCK 
 
 template <int TASK, int GEOM> cudaError_t launch_step(const ModelConst &M, const StepArgs &A, cudaStream_t s) {
     constexpr int B = Blk<GEOM>::STEP;
-#if defined(URGYM_STEP_TILES) && URGYM_STEP_TILES > 1
-    if (URGYM_BASE(GEOM) == GEOM_CAPSULE) {
-        const int64_t per = 32 * URGYM_STEP_TILES;
-        urgym_step_kernel_mt<TASK, GEOM><<<(unsigned)((A.n + per - 1) / per), 32, step_mt_smem_bytes<TASK, GEOM>(), s>>>(M, A);
-        return cudaGetLastError();
-    }
-#endif
     urgym_step_kernel<TASK, GEOM><<<(unsigned)((A.n + B - 1) / B), B, step_smem_bytes<TASK, GEOM>(), s>>>(M, A);
     return cudaGetLastError();
 }
@@ -1050,12 +857,6 @@ template <int TASK, int GEOM> cudaError_t launch_refresh(const ModelConst &M, co
 template <int TASK, int GEOM> cudaError_t prepare_kernels(const ModelConst &, const AuxArgs &, cudaStream_t) {
     cudaError_t e = cudaFuncSetAttribute(urgym_step_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes<TASK, GEOM>());
     if (e != cudaSuccess) return e;
-#if defined(URGYM_STEP_TILES) && URGYM_STEP_TILES > 1
-    if (URGYM_BASE(GEOM) == GEOM_CAPSULE) {
-        e = cudaFuncSetAttribute(urgym_step_kernel_mt<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_mt_smem_bytes<TASK, GEOM>());
-        if (e != cudaSuccess) return e;
-    }
-#endif
     e = cudaFuncSetAttribute(urgym_reset_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)reset_smem_bytes<TASK, GEOM>());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(urgym_autoreset_kernel<TASK, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)autoreset_smem_bytes<TASK, GEOM>());
