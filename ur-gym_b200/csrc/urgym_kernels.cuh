@@ -124,12 +124,8 @@ __device__ __forceinline__ void load_vel(const StateView &st, int64_t i, float *
 __device__ __forceinline__ void store_vel(const StateView &st, int64_t i, const float *vel) {
     st_group(st.v8 + 2 * i, make_float4(vel[0], vel[1], vel[2], vel[3]), make_float4(vel[4], vel[5], 0.0f, 0.0f));
 }
-template <int TASK> __device__ __forceinline__ void load_dyn(const StateView &st, int64_t i, EnvState &s) {
-    float4 a, b;
-    ld_group(st.q8 + 2 * i, a, b);
-    s.q[0] = a.x; s.q[1] = a.y; s.q[2] = a.z; s.q[3] = a.w; s.q[4] = b.x; s.q[5] = b.y;
-    s.elapsed = __float_as_int(b.z);
-    s.ep_ret = b.w;
+// link_dist = last_dist: read by the observation row and the reward, i.e. late in the step
+template <int TASK> __device__ __forceinline__ void load_ld(const StateView &st, int64_t i, EnvState &s) {
     if (Traits<TASK>::HAS_OBST) {
         float4 l = st.ld4[i];
         s.ld[0] = l.x; s.ld[1] = l.y; s.ld[2] = l.z; s.ld[3] = l.w; s.ld[4] = st.ld1[i];
@@ -137,6 +133,14 @@ template <int TASK> __device__ __forceinline__ void load_dyn(const StateView &st
 #pragma unroll
         for (int k = 0; k < 5; k++) s.ld[k] = 0.0f;
     }
+}
+template <int TASK> __device__ __forceinline__ void load_dyn(const StateView &st, int64_t i, EnvState &s) {
+    float4 a, b;
+    ld_group(st.q8 + 2 * i, a, b);
+    s.q[0] = a.x; s.q[1] = a.y; s.q[2] = a.z; s.q[3] = a.w; s.q[4] = b.x; s.q[5] = b.y;
+    s.elapsed = __float_as_int(b.z);
+    s.ep_ret = b.w;
+    load_ld<TASK>(st, i, s);
 }
 template <int TASK> __device__ __forceinline__ void store_dyn(const StateView &st, int64_t i, const EnvState &s) {
     st_group(st.q8 + 2 * i, make_float4(s.q[0], s.q[1], s.q[2], s.q[3]),
@@ -337,31 +341,40 @@ __global__ void __launch_bounds__(Blk<GEOM>::STEP, Blk<GEOM>::STEP_MINBLOCKS) ur
     HullTasks *s_tasks = reinterpret_cast<HullTasks *>(s_hull + URGYM_HULL_BLOB_F4);      // hull geometry only
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (blockIdx.x == 0 && tid == 0) {                          // this launch is reset event number event[chain] + 1
-        if (A.bump == 1) A.event[A.chain] += 1u;
-        if (A.bump == 2) {      // a whole step: one logical event for all chains (lagging chain counters catch up)
-            uint32_t m = 0u;
-            for (int c = 0; c < URGYM_MAX_CHAINS; c++) m = A.event[c] > m ? A.event[c] : m;
-            for (int c = 0; c < URGYM_MAX_CHAINS; c++) A.event[c] = m + 1u;
-        }
-    }
     const float4 *hv = stage_hull<GEOM>(A.hull, s_hull);
     if (HULL) {
         if (tid < 4) s_tasks->count[tid] = 0;
         __syncthreads();
     }
 
-    const int64_t wbase = (int64_t)blockIdx.x * B + warp * W;                 // first env of this warp
-    if (!HULL && wbase >= A.n) return;                       // (hull geometry: every warp of the block takes part in its barriers)
-    // (the capsule kernels keep the plain expressions: the extra selects of the hull form cost UR5StaReach 9 % -- ptxas
-    // schedules the whole kernel differently around them)
-    const int rows = HULL ? (wbase >= A.n ? 0 : ((A.n - wbase) < W ? (int)(A.n - wbase) : W)) : ((A.n - wbase) < W ? (int)(A.n - wbase) : W);
+    // Env indices of a launch fit 32 bits (the launcher checks it).  With 32-bit index arithmetic every plane address is one
+    // IMAD.WIDE.U32 instead of an IADD3 / IADD3.X pair and the loads issue ~8 instructions earlier: UR5OriReach -2.6 %,
+    // UR5DynReach -0.5 %, UR5ObsReach -0.15 %; UR5StaReach +0.5 % (ptxas schedules it differently), which keeps 64 bits.
+#ifdef URGYM_IDX32
+    constexpr bool IDX32 = URGYM_IDX32 != 0;
+#else
+    constexpr bool IDX32 = !HULL && TASK != TASK_STA;
+#endif
+    int64_t wbase, i;
+    int rows;
+    if (IDX32) {
+        const unsigned n32 = (unsigned)A.n, wb32 = blockIdx.x * (unsigned)B + (unsigned)(warp * W);
+        if (wb32 >= n32) return;
+        wbase = wb32;
+        rows = (n32 - wb32) < (unsigned)W ? (int)(n32 - wb32) : W;
+        i = wb32 + (unsigned)(lane < rows ? lane : rows - 1);
+    } else {
+        wbase = (int64_t)blockIdx.x * B + warp * W;               // first env of this warp
+        if (!HULL && wbase >= A.n) return;                       // (hull geometry: every warp of the block takes part in its barriers)
+        // (the capsule kernels keep the plain expressions: the extra selects of the hull form cost UR5StaReach 9 % -- ptxas
+        // schedules the whole kernel differently around them)
+        rows = HULL ? (wbase >= A.n ? 0 : ((A.n - wbase) < W ? (int)(A.n - wbase) : W)) : ((A.n - wbase) < W ? (int)(A.n - wbase) : W);
+        i = HULL ? (lane < rows ? wbase + lane : (rows ? wbase + rows - 1 : A.n - 1)) : wbase + (lane < rows ? lane : rows - 1);
+    }
     float *s_obs = s_tiles + warp * W * TF;
     float *s_scr = s_obs + lane;                              // capsule scratch: column `lane` of a [41][32] block
-
     // every lane runs the step (warp-level barriers inside); lanes past the end redo the last env and store nothing
     const bool live = lane < rows;
-    const int64_t i = HULL ? (live ? wbase + lane : (rows ? wbase + rows - 1 : A.n - 1)) : wbase + (live ? lane : rows - 1);
     EnvState s;
     StepOut o;
     float vel[6], act[6];
@@ -376,8 +389,18 @@ __global__ void __launch_bounds__(Blk<GEOM>::STEP, Blk<GEOM>::STEP_MINBLOCKS) ur
             for (int k = 0; k < 6; k++) act[k] = __ldg(ga + k);
         }
     }
+    load_hot<TASK>(A.st, i, s);         // first: the obstacle pose is the first thing computed (UR5DynReach -0.3 %, others +-0)
     load_dyn<TASK>(A.st, i, s);
-    load_hot<TASK>(A.st, i, s);
+    // (after the loads have been issued: ahead of them, this branch and its reconvergence point delayed every warp's loads;
+    // moved here: UR5ObsReach -2.5 %, UR5OriReach -1.0 %, UR5StaReach -0.5 %, UR5DynReach -0.4 % kernel time)
+    if (blockIdx.x == 0 && tid == 0) {                          // this launch is reset event number event[chain] + 1
+        if (A.bump == 1) A.event[A.chain] += 1u;
+        if (A.bump == 2) {      // a whole step: one logical event for all chains (lagging chain counters catch up)
+            uint32_t m = 0u;
+            for (int c = 0; c < URGYM_MAX_CHAINS; c++) m = A.event[c] > m ? A.event[c] : m;
+            for (int c = 0; c < URGYM_MAX_CHAINS; c++) A.event[c] = m + 1u;
+        }
+    }
     if (HULL) {
         float3 oe;
         float velv[6], ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -822,6 +845,7 @@ static inline unsigned grid_for(int64_t n) { return (unsigned)((n + URGYM_BLOCK 
 
 template <int TASK, int GEOM> cudaError_t launch_step(const ModelConst &M, const StepArgs &A, cudaStream_t s) {
     constexpr int B = Blk<GEOM>::STEP;
+    if (A.n <= 0 || A.n > 0x7FFFFFFFll) return cudaErrorInvalidValue;        // the kernel's env indices are 32-bit
     urgym_step_kernel<TASK, GEOM><<<(unsigned)((A.n + B - 1) / B), B, step_smem_bytes<TASK, GEOM>(), s>>>(M, A);
     return cudaGetLastError();
 }
