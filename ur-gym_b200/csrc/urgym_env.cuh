@@ -737,17 +737,21 @@ URGYM_HD ObstW env_step_begin(EnvState &s, const float *act, float *row, float *
     }
     return O;
 }
-template <int TASK>
+// `done_hook(finished)` is called (by every lane, converged) as soon as it is known whether the episode ends with this step:
+// the step kernel reserves its auto-reset queue entries there, ~150 instructions before it needs the reply.
+struct NoDoneHook { URGYM_HD void operator()(bool) const {} };
+template <int TASK, class DoneHook = NoDoneHook>
 URGYM_HD void env_step_finish(EnvState &s, float *row, const float *ee, const float *dist, bool coll, const ObstW &O, float3 oe,
-                              const float *vel, StepOut &o) {
-    // 4. observation: carries link_dist from BEFORE this step's reward (quirk Q1)               core.py:311
-    write_obs_row<TASK>(row, ee, s.q, s.E, O, oe, vel, s.ld);
-    // 5. termination                                                                           core.py:313-315
+                              const float *vel, StepOut &o, DoneHook done_hook = DoneHook()) {
+    // 5. termination (computed ahead of the observation row, which does not depend on it)      core.py:313-315
     float d, ang;
     bool succ = goal_metrics<TASK>(ee, s.E, s.C, d, ang);
     o.collision = coll;
     o.terminated = succ || coll;
     o.success = o.terminated && !coll;
+    done_hook(o.terminated || s.elapsed + 1 >= URGYM_MAX_STEPS);
+    // 4. observation: carries link_dist from BEFORE this step's reward (quirk Q1)               core.py:311
+    write_obs_row<TASK>(row, ee, s.q, s.E, O, oe, vel, s.ld);
     // 6. reward                                                                                core.py:316
     float r;
     if (TASK == TASK_ORI) {             // reach.py:221-236
@@ -783,9 +787,9 @@ URGYM_HD void env_step_finish(EnvState &s, float *row, const float *ee, const fl
     o.truncated = s.elapsed >= URGYM_MAX_STEPS;
     s.ep_ret += r;
 }
-template <int TASK, int GEOM>
+template <int TASK, int GEOM, class DoneHook = NoDoneHook>
 URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const float4 *hv, float *row, StepOut &o,
-                       float *vel_out, float *scratch, int cs) {
+                       float *vel_out, float *scratch, int cs, DoneHook done_hook = DoneHook()) {
     float3 oe;
     float vel[6];
     const ObstW O = env_step_begin<TASK, GEOM>(s, act, row, vel_out, vel, oe);
@@ -793,7 +797,7 @@ URGYM_HD void env_step(const ModelConst &M, EnvState &s, const float *act, const
     float ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     bool coll = robot_pass<TASK, GEOM>(M, s.q, row + 6, O, hv, true, ee, dist, scratch, cs);
     URGYM_WARP_SYNC();      // every lane is done with the scratch before observation rows are written over it
-    env_step_finish<TASK>(s, row, ee, dist, coll, O, oe, vel, o);
+    env_step_finish<TASK>(s, row, ee, dist, coll, O, oe, vel, o, done_hook);
 }
 
 // RobotTaskEnv._get_obs (core.py:252-261) from the current state, no stepping.  stale_vel: ReachDyn.velocity as

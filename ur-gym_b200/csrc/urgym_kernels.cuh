@@ -402,15 +402,27 @@ __global__ void __launch_bounds__(Blk<GEOM>::STEP, Blk<GEOM>::STEP_MINBLOCKS) ur
             for (int c = 0; c < URGYM_MAX_CHAINS; c++) A.event[c] = m + 1u;
         }
     }
+    // auto-reset queue: one reservation per warp that finished envs, made as soon as the flags are known (env_step_finish
+    // calls the hook ahead of the observation row and the reward); the reply is needed only at the very end
+    unsigned done_mask = 0u, qbase = 0u;
+    auto reserve = [&](bool finished) {
+        done_mask = __ballot_sync(0xffffffffu, live && finished);
+        // (inline PTX: around atomicAdd the compiler builds its own warp aggregation, whose shuffle waits for the reply at once)
+        // (the count goes through a shuffle so that ptxas does not see a warp-uniform operand: around a uniform atomic it builds
+        // its own warp aggregation, whose shuffle waits for the reply at once)
+        // (`+ threadIdx.y`, which is 0: around an atomic whose address it can prove warp-uniform ptxas builds its own warp
+        // aggregation, and the shuffle of that aggregation waits for the reply at once -- 2.7-4.2 % of a warp's life)
+        if (A.queue && done_mask && lane == 0) qbase = atomicAdd(A.qcount + threadIdx.y, (unsigned)__popc(done_mask));
+    };
     if (HULL) {
         float3 oe;
         float velv[6], ee[6], dist[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         const ObstW O = env_step_begin<TASK, GEOM>(s, act, s_obs + lane * D, vel, velv, oe);
         const bool coll = hull_pass_phased<TASK, GEOM>(c_model, s_tiles, tid, O, hv, ee, dist, *s_tasks);
-        env_step_finish<TASK>(s, s_obs + lane * D, ee, dist, coll, O, oe, velv, o);
+        env_step_finish<TASK>(s, s_obs + lane * D, ee, dist, coll, O, oe, velv, o, reserve);
         if (rows == 0) return;
     } else {
-        env_step<TASK, GEOM>(c_model, s, act, hv, s_obs + lane * D, o, vel, s_scr, W);
+        env_step<TASK, GEOM>(c_model, s, act, hv, s_obs + lane * D, o, vel, s_scr, W, reserve);
     }
     if (live) {
         store_dyn<TASK>(A.st, i, s);
@@ -432,10 +444,6 @@ __global__ void __launch_bounds__(Blk<GEOM>::STEP, Blk<GEOM>::STEP_MINBLOCKS) ur
         }
         if (lane == 0) stat_add(slot + 6, (unsigned long long)rows);
     }
-    // auto-reset queue: one reservation per warp that finished envs (the reply is needed only at the very end)
-    const unsigned done_mask = __ballot_sync(0xffffffffu, live && (o.terminated || o.truncated));
-    unsigned qbase = 0u;
-    if (A.queue && done_mask && lane == 0) qbase = atomicAdd(A.qcount, (unsigned)__popc(done_mask));
     __syncwarp();
     // observation tile -> global, 16-byte vectorised
     float *gobs = A.obs + wbase * D;
