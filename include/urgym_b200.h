@@ -83,6 +83,7 @@ enum { URGYM_F_Q = 0,            /* float [N,6]  joint angles                   
  * `seed` keys the counter-based reset stream (Philox4x32-10): the draws of a reset depend on (seed, global env
  * index, reset event), where the reset event is the handle's count of urgym_step/urgym_reset calls so far -- not on
  * the sharding, so 1/2/4/8-GPU runs that issue the same calls produce the same episodes.
+ * n_envs < 2^31 per handle (URGYM_EINVAL otherwise; env_index_offset is 64-bit: shard larger batches over handles).
  * All envs start un-reset: call urgym_reset(h, NULL, ...) once.   Replaces: gymnasium.make(id)
  * (ur_tasks.py:37-90: PyBullet(...) + UR5Ori(...) + Reach*(...)). */
 int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_envs, int64_t env_index_offset,

@@ -45,6 +45,8 @@ def test_no_cpu_fallback():
     h = ctypes.c_void_p()
     assert L.urgym_create(ctypes.byref(h), 0, 1, 4, 0, 0, 0) == -2          # URGYM_ENODEVICE
     assert b"no CPU path" in L.urgym_last_error(None)
+    assert L.urgym_create(ctypes.byref(h), 0, 1, ctypes.c_int64(1 << 31), 0, 0, 0) == -1     # URGYM_EINVAL: 32-bit env indices per handle
+    assert b"2^31" in L.urgym_last_error(None)
     # the motor-driven env has no CPU path either
     with pytest.raises(ug.UrgymError):
         ug.UR5MotorVecEnv(4)

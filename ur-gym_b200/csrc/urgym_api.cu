@@ -184,6 +184,9 @@ extern "C" int urgym_create(urgym_env_t **out, int task, int geom, int64_t n_env
     if (task < 0 || task > 3) return fail(nullptr, URGYM_EINVAL, "urgym_create: task must be 0..3%s", "");
     if (geom != URGYM_GEOM_HULL && geom != URGYM_GEOM_CAPSULE) return fail(nullptr, URGYM_EINVAL, "urgym_create: bad geom%s", "");
     if (n_envs <= 0 || env_index_offset < 0) return fail(nullptr, URGYM_EINVAL, "urgym_create: n_envs must be > 0 and offset >= 0%s", "");
+    // env indices inside a handle are 32-bit (the kernels' index arithmetic; 2^31 envs would need 2 TB of state anyway); the
+    // GLOBAL index offset + i of the reset stream stays 64-bit
+    if (n_envs > 0x7FFFFFFFll) return fail(nullptr, URGYM_EINVAL, "urgym_create: n_envs must be < 2^31 per handle (shard over more handles)%s", "");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
