@@ -33,3 +33,20 @@ def test_spatial_profile_matches_published(env_id):
     from tests.closed_loop import compare_profiles
     zs, zf, mean_diff, corr = compare_profiles(r)
     assert abs(r["success_rate_pct"] - r["published"]["published_success_rate_pct"]) <= 3.0, r
+
+
+@pytest.mark.parametrize("env_id", ALL)
+def test_success_step_histogram_matches_published(env_id):
+    """How many steps the successful episodes take, as a distribution: the histogram of the published per-episode lines
+    (bins 0-3-5-7-9-12-16-25-50-100, tests/golden/make_policy_fixtures.py) against ~5 000 episodes of the host instantiation
+    (the reference's scenario grid for UR5OriReach / UR5DynReach, natural resets for UR5ObsReach / UR5StaReach).  Total
+    variation distance <= 0.06 (observed 0.013 / 0.023 / 0.039 / 0.016; sampling noise of two 5 000-episode histograms ~0.015):
+    the step size 0.1 pi, the success thresholds and the geometry the policies steer by act on every one of those steps."""
+    import numpy as np
+    grid = env_id in ("UR5OriReach-v1", "UR5DynReach-v1")
+    r = run_host(env_id, geom=1, n=5000, grid=grid, link_dist_mode=1 if POLICY_LINK_DIST[env_id] == "workbench" else 0)
+    a = np.asarray(r["published"]["published_success_step_hist"], float)
+    b = np.asarray(r["success_step_hist"], float)
+    tv = 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
+    assert tv <= 0.06, (tv, a.tolist(), b.tolist())
+    assert abs(r["collision_mean_steps"] - r["published"]["published_collision_mean_steps"]) <= 2.0, r
