@@ -50,3 +50,9 @@ def test_success_step_histogram_matches_published(env_id):
     tv = 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
     assert tv <= 0.06, (tv, a.tolist(), b.tolist())
     assert abs(r["collision_mean_steps"] - r["published"]["published_collision_mean_steps"]) <= 2.0, r
+    if env_id != "UR5StaReach-v1":
+        # the reward sums of the successful episodes (they contain every per-step term of compute_reward, for UR5ObsReach
+        # the 100 x link-distance differences too): observed -103.2 / -184.5 / -98.6 against -103.0 / -183.1 / -99.0 published.
+        # (UR5StaReach's published sums are ~29 lower than any variant here produces: DESIGN.md section 2.1-6, not claimed)
+        pub = r["published"]["published_success_mean_reward"]
+        assert abs(r["success_mean_reward"] - pub) <= 0.02 * abs(pub), (r["success_mean_reward"], pub)
